@@ -45,6 +45,6 @@ def check_record(name, t, rec, gold, planes=None):
             if key in planes and planes[key] is not None:
                 assert sha(planes[key]) == gold[key], f"{where}: plane {key} differs from the reference"
     assert [float(a) for a in rec["areas"]] == gold["areas"], f"{where}: contour areas"
-    assert [list(b) for b in rec["boxes"]] == gold["boxes"], f"{where}: bounding boxes"
+    assert [list(b) for b in rec["boxes"]] == [list(b) for b in gold["boxes"]], f"{where}: bounding boxes"
     for key in DECISION_KEYS:
         assert rec[key] == gold[key], f"{where}: {key} {rec[key]} != {gold[key]}"
