@@ -1,0 +1,134 @@
+// Shared declarations of libfmgpu.so (sm_100a only).  See include/fm_gpu.h for the C ABI and
+// DESIGN.md for the data layout.  Arithmetic follows SURVEY.md Appendix A (verified against the
+// reference's cv2 call chain, find_motion/find_motion.py:487-494, 619-700, 549-589).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fm_gpu.h"
+
+#define FM_MAX_K 1024          // widest supported Gaussian (taps)
+#define FM_TILE_PX 512         // pixels per background tile: 32 lanes x 16 px
+#define FM_TILE_WORDS 16       // 32-bit threshold words per tile
+
+struct StreamState {           // per stream, device resident (find_motion.py:362-371)
+    int has_bg;                // ref_frame is not None
+    int counter;               // movement_counter
+    int decay;                 // movement_decay
+    int cache_len;             // len(frame_cache)
+};
+
+struct ResizeTab {             // INTER_AREA decimation tables of one axis
+    int *start;                // [dst+1] prefix offsets into idx/wt
+    int *idx;                  // source index per tap
+    float *wt;                 // float32 weight per tap
+    int max_taps;
+};
+
+struct CclScratch {            // run-based labelling scratch for `frames` frames at a time
+    int frames;                // sub-batch capacity
+    int cap;                   // run slots per row
+    size_t slots;              // per frame: h * cap
+    uint16_t *xs, *xe;         // [frames][slots]
+    int *rowcnt;               // [frames][h]
+    int *parent;               // [frames][1 + slots]   (id 0 = the outside of the image)
+    int *area2;                // [frames][slots]
+    int *bbox;                 // [frames][slots][4]  xmin, ymin, xmax, ymax
+};
+
+struct fm_ctx {
+    fm_config cfg;
+    fm_info info;
+    int S, Tmax, W, H, w, h, k, wpr;
+    int N;                     // w*h
+    int ntiles;                // ceil(N / FM_TILE_PX)
+    int resize_mode;           // 0 identity, 1 general tables, 2 integer ratio
+    int fx, fy;                // integer ratios (mode 2)
+    int maxc;
+    // tables
+    int *coef;                 // [k] 8.8 fixed-point Gaussian taps
+    ResizeTab xtab, ytab;
+    // planes
+    uint8_t *gray;             // [S][Tmax][h][w]
+    uint16_t *hor;             // [S][Tmax][h][w]  horizontal pass (generic blur)
+    uint8_t *blur;             // [S][Tmax][h][w]  masked blur
+    double *bg;                // [S][ntiles][8][32][2]  float64 background, tiled
+    uint32_t *maskbits;        // [S][h][wpr]  1 = zero the blur here
+    uint32_t *maskflat;        // [S][ntiles*16] same mask, flat bit order (fused kernels)
+    uint32_t *tflat;           // [S][Tmax][ntiles*16]  raw threshold, flat bit order
+    uint32_t *dil;             // [S][Tmax][h][wpr]  dilated threshold, row-padded bit plane
+    uint32_t *fill;            // [S][Tmax][h][wpr]  dilated threshold with holes filled
+    int *any;                  // [S][Tmax] frame has any set pixel
+    int *ncomp;                // [S][Tmax]
+    int *ncounted;             // [S][Tmax]
+    fm_component *comps;       // [S][Tmax][maxc]
+    fm_frame_stats *stats;     // [S][Tmax]
+    StreamState *state;        // [S]
+    int *errflag;              // device error word (capacity overflow)
+    CclScratch ccl;
+    int *spans;                // mask raster scratch [h][2]
+    int last_T;                // frames per stream of the last call
+    bool planes_valid;
+    // host staging for fm_process_host
+    uint8_t *stage_dev;
+    size_t stage_bytes;
+    fm_frame_stats *stats_pinned;
+    cudaStream_t own_stream;
+    // timing
+    bool timing;
+    cudaEvent_t ev[4];
+    double t_ms[3];
+    int64_t t_calls;
+};
+
+extern unsigned long long g_launches;
+void fm_set_error(const char *fmt, ...);
+
+#define FM_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            fm_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                         __LINE__);                                                       \
+            return FM_ECUDA;                                                              \
+        }                                                                                 \
+    } while (0)
+
+#define FM_LAUNCH_CHECK()                                                         \
+    do {                                                                          \
+        g_launches++;                                                             \
+        cudaError_t e_ = cudaGetLastError();                                      \
+        if (e_ != cudaSuccess) {                                                  \
+            fm_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), \
+                         __FILE__, __LINE__);                                     \
+            return FM_ECUDA;                                                      \
+        }                                                                         \
+    } while (0)
+
+// stage launchers (each enqueues on `st`, returns FM_OK / error)
+int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
+                       cudaStream_t st);
+int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st);
+int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
+                    cudaStream_t st);
+int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
+int fm_launch_masks(fm_ctx *c, int stream, int n_polys, const int *offs, const int *pts_scaled,
+                    int npts, cudaStream_t st);
+int fm_launch_bg_export(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
+int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st);
+int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st);
+int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);
+void fm_ccl_free(CclScratch *s);
+int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out,
+                 int *n);
+
+__device__ __forceinline__ int fm_reflect101(int i, int n) {
+    // BORDER_REFLECT_101 for any offset
+    if ((unsigned)i < (unsigned)n) return i;
+    if (n == 1) return 0;
+    int p = 2 * (n - 1);
+    i %= p;
+    if (i < 0) i += p;
+    return i >= n ? p - i : i;
+}

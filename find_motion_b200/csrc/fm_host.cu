@@ -1,0 +1,487 @@
+// Host side of libfmgpu.so: context life cycle, parameter derivation exactly as the reference
+// computes it (find_motion/find_motion.py:334-335, 406, 422-423, 482-484), table
+// construction (Gaussian taps A.3, INTER_AREA taps A.1) and the C-ABI entry points of
+// include/fm_gpu.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fm_common.cuh"
+
+unsigned long long g_launches = 0;
+static thread_local char g_err[512] = "";
+
+void fm_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *fm_last_error(void) { return g_err; }
+extern "C" int fm_version(void) { return 100; }
+extern "C" uint64_t fm_launch_count(void) { return g_launches; }
+
+// --------------------------------------------------------------------------------------------
+// tables
+// --------------------------------------------------------------------------------------------
+static std::vector<int> gauss_coeffs(int k) {
+    // cv2.getGaussianKernel(k, sigma<=0) quantised to 8 fractional bits with error diffusion
+    std::vector<double> kern(k);
+    static const double small[4][7] = {{1.0},
+                                       {0.25, 0.5, 0.25},
+                                       {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                                       {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125}};
+    if (k <= 7) {
+        for (int i = 0; i < k; i++) kern[i] = small[k >> 1][i];
+    } else {
+        double sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8;
+        double scale2x = -0.5 / (sigma * sigma);
+        double sum = 0.0;
+        for (int i = 0; i < k; i++) {
+            double x = i - (k - 1) * 0.5;
+            kern[i] = exp(scale2x * x * x);
+            sum += kern[i];
+        }
+        double inv = 1.0 / sum;
+        for (int i = 0; i < k; i++) kern[i] *= inv;
+    }
+    std::vector<int> c(k, 0);
+    double err = 0.0;
+    int tot = 0;
+    for (int i = 0; i < k / 2; i++) {
+        double adj = kern[i] * 256.0 + err;
+        int v = (int)nearbyint(adj);          // round half to even (default rounding mode)
+        err = adj - v;
+        c[i] = c[k - 1 - i] = v;
+        tot += 2 * v;
+    }
+    c[k / 2] = 256 - tot;
+    return c;
+}
+
+struct HostTab {
+    std::vector<int> start, idx;
+    std::vector<float> wt;
+    int max_taps = 0;
+};
+
+static HostTab area_tab(int src, int dst) {
+    HostTab t;
+    double scale = 1.0 / ((double)dst / (double)src);
+    t.start.push_back(0);
+    for (int d = 0; d < dst; d++) {
+        double f1 = d * scale, f2 = f1 + scale;
+        double cell = std::min(scale, (double)src - f1);
+        int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+        s2 = std::min(s2, src - 1);
+        s1 = std::min(s1, s2);
+        if (s1 - f1 > 1e-3) {
+            t.idx.push_back(s1 - 1);
+            t.wt.push_back((float)((s1 - f1) / cell));
+        }
+        for (int s = s1; s < s2; s++) {
+            t.idx.push_back(s);
+            t.wt.push_back((float)(1.0 / cell));
+        }
+        if (f2 - s2 > 1e-3) {
+            t.idx.push_back(s2);
+            t.wt.push_back((float)(std::min(std::min(f2 - s2, 1.0), cell) / cell));
+        }
+        t.max_taps = std::max(t.max_taps, (int)t.idx.size() - t.start.back());
+        t.start.push_back((int)t.idx.size());
+    }
+    return t;
+}
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &v) {
+    FM_CUDA(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) FM_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FM_OK;
+}
+
+static int upload_tab(ResizeTab *d, const HostTab &h) {
+    int rc;
+    if ((rc = upload(&d->start, h.start))) return rc;
+    if ((rc = upload(&d->idx, h.idx))) return rc;
+    if ((rc = upload(&d->wt, h.wt))) return rc;
+    d->max_taps = h.max_taps;
+    return FM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------
+extern "C" int fm_ctx_destroy(fm_ctx *c) {
+    if (!c) return FM_OK;
+    cudaSetDevice(c->cfg.device);
+    cudaFree(c->coef);
+    cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
+    cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
+    cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
+    cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
+    cudaFree(c->any); cudaFree(c->ncomp); cudaFree(c->ncounted); cudaFree(c->comps); cudaFree(c->stats);
+    cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->stage_dev);
+    fm_ccl_free(&c->ccl);
+    if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (int i = 0; i < 4; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+    return FM_OK;
+}
+
+extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
+    if (!cfg || !out) { fm_set_error("null argument"); return FM_EINVAL; }
+    *out = nullptr;
+    if (cfg->n_streams < 1 || cfg->frame_width < 1 || cfg->frame_height < 1 || cfg->max_frames < 1 ||
+        cfg->box_size < 1 || cfg->blur_scale < 1 || cfg->min_box_scale < 1 || cfg->fps < 0) {
+        fm_set_error("invalid configuration (streams/geometry/max_frames/box_size/blur_scale/min_box_scale)");
+        return FM_EINVAL;
+    }
+    if (cfg->box_size > cfg->frame_width) {
+        // INTER_AREA with a destination wider than the source is a bilinear-style upscale in cv2
+        // that this library does not reproduce
+        fm_set_error("box_size %d > frame width %d: upscaling resize is not supported", cfg->box_size,
+                     cfg->frame_width);
+        return FM_ERANGE;
+    }
+    int ndev = 0;
+    FM_CUDA(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        fm_set_error("CUDA device %d not present (%d devices)", cfg->device, ndev);
+        return FM_ECUDA;
+    }
+    FM_CUDA(cudaSetDevice(cfg->device));
+
+    fm_ctx *c = new fm_ctx();
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->S = cfg->n_streams; c->Tmax = cfg->max_frames;
+    c->W = cfg->frame_width; c->H = cfg->frame_height;
+    // derived parameters, mirroring the Python expressions (true division on floats, int() truncation)
+    const double W = c->W, H = c->H, box = cfg->box_size;
+    c->w = cfg->box_size;
+    c->h = (int)(H * (box / W));                                   // imutils.resize
+    int g = (int)(box / (double)cfg->blur_scale);                  // find_motion.py:482
+    c->k = (g % 2 == 0) ? g + 1 : g;                               // :483
+    fm_info &inf = c->info;
+    inf.proc_width = c->w; inf.proc_height = c->h; inf.gaussian = c->k;
+    inf.min_area = (int)pow(box / (double)cfg->min_box_scale, 2.0);    // :406
+    inf.scale = box / W;                                           // :422
+    inf.max_area = (int)((W * H) / 2.0 * inf.scale);               // :423
+    inf.cache_frames = (int)(cfg->cache_time * cfg->fps);          // :334
+    inf.min_movement_frames = (int)(cfg->min_time * cfg->fps);     // :335
+    if (c->h < 1) { fm_set_error("processing height is zero"); delete c; return FM_ERANGE; }
+    if (c->k > FM_MAX_K) { fm_set_error("gaussian size %d too large", c->k); delete c; return FM_ERANGE; }
+    if (c->w > 65535 || c->h > 65535) { fm_set_error("processing plane too large"); delete c; return FM_ERANGE; }
+    c->wpr = (c->w + 31) / 32;
+    inf.words_per_row = c->wpr;
+    c->N = c->w * c->h;
+    c->ntiles = (c->N + FM_TILE_PX - 1) / FM_TILE_PX;
+    c->maxc = cfg->max_components > 0 ? cfg->max_components : 256;
+
+    int rc = FM_OK;
+    auto fail = [&](int code) { fm_ctx_destroy(c); return code; };
+
+    // resize mode (cv2::resize INTER_AREA dispatch)
+    if (c->w == c->W && c->h == c->H) {
+        c->resize_mode = 0;
+    } else {
+        if (c->h > c->H) { fm_set_error("upscaling resize is not supported"); return fail(FM_ERANGE); }
+        double sx = 1.0 / ((double)c->w / W), sy = 1.0 / ((double)c->h / H);
+        int isx = (int)nearbyint(sx), isy = (int)nearbyint(sy);
+        bool fast = fabs(sx - isx) < 2.220446049250313e-16 && fabs(sy - isy) < 2.220446049250313e-16;
+        if (fast) {
+            c->resize_mode = 2; c->fx = isx; c->fy = isy;
+        } else {
+            c->resize_mode = 1;
+            if ((rc = upload_tab(&c->xtab, area_tab(c->W, c->w)))) return fail(rc);
+            if ((rc = upload_tab(&c->ytab, area_tab(c->H, c->h)))) return fail(rc);
+        }
+    }
+    inf.front_end = c->resize_mode == 0 ? 1 : 2;
+    if ((rc = upload(&c->coef, gauss_coeffs(c->k)))) return fail(rc);
+
+    const size_t F = (size_t)c->S * c->Tmax;
+    const size_t flatw = (size_t)c->ntiles * FM_TILE_WORDS;
+#define ALLOC(ptr, bytes)                                                                 \
+    do {                                                                                  \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                            \
+        if (e_ != cudaSuccess) {                                                          \
+            fm_set_error("cudaMalloc(%zu bytes) for %s failed: %s", (size_t)(bytes), #ptr, \
+                         cudaGetErrorString(e_));                                         \
+            return fail(FM_ENOMEM);                                                       \
+        }                                                                                 \
+    } while (0)
+    ALLOC(c->gray, F * c->N);
+    ALLOC(c->hor, F * c->N * sizeof(uint16_t));
+    ALLOC(c->blur, F * c->N + 64);
+    ALLOC(c->bg, (size_t)c->S * c->ntiles * FM_TILE_PX * sizeof(double));
+    ALLOC(c->maskbits, (size_t)c->S * c->h * c->wpr * 4);
+    ALLOC(c->maskflat, (size_t)c->S * flatw * 4);
+    ALLOC(c->tflat, (F * flatw + FM_TILE_WORDS) * 4);
+    ALLOC(c->dil, F * c->h * c->wpr * 4);
+    ALLOC(c->fill, F * c->h * c->wpr * 4);
+    ALLOC(c->any, F * sizeof(int));
+    ALLOC(c->ncomp, F * sizeof(int));
+    ALLOC(c->ncounted, F * sizeof(int));
+    ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
+    ALLOC(c->stats, F * sizeof(fm_frame_stats));
+    ALLOC(c->state, (size_t)c->S * sizeof(StreamState));
+    ALLOC(c->errflag, sizeof(int));
+    FM_CUDA(cudaMemset(c->maskbits, 0, (size_t)c->S * c->h * c->wpr * 4));
+    FM_CUDA(cudaMemset(c->maskflat, 0, (size_t)c->S * flatw * 4));
+    FM_CUDA(cudaMemset(c->tflat, 0, (F * flatw + FM_TILE_WORDS) * 4));
+    FM_CUDA(cudaMemset(c->bg, 0, (size_t)c->S * c->ntiles * FM_TILE_PX * sizeof(double)));
+    FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
+    FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
+    // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
+    // most w/4 + 2 runs of either polarity; sub-batch sized to ~1.5 GB
+    int cap = c->w / 4 + 3;
+    size_t per_frame = (size_t)c->h * cap * 28 + (size_t)c->h * 4 + 4;
+    size_t budget = (size_t)1536 << 20;
+    int nb = (int)std::min<size_t>(F, std::max<size_t>(1, budget / per_frame));
+    if ((rc = fm_ccl_alloc(&c->ccl, nb, c->h, cap))) return fail(rc);
+    FM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) FM_CUDA(cudaEventCreate(&c->ev[i]));
+    *out = c;
+    return FM_OK;
+}
+
+extern "C" int fm_ctx_info(const fm_ctx *c, fm_info *info) {
+    if (!c || !info) { fm_set_error("null argument"); return FM_EINVAL; }
+    *info = c->info;
+    return FM_OK;
+}
+
+extern "C" int fm_ctx_reset(fm_ctx *c, int stream) {
+    if (!c) { fm_set_error("null context"); return FM_EINVAL; }
+    if (stream >= c->S) { fm_set_error("stream %d out of range", stream); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaDeviceSynchronize());
+    if (stream < 0)
+        FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
+    else
+        FM_CUDA(cudaMemset(c->state + stream, 0, sizeof(StreamState)));
+    return FM_OK;
+}
+
+extern "C" int fm_ctx_set_masks(fm_ctx *c, int stream, int n_polys, const int32_t *poly_offsets,
+                                const int32_t *xy) {
+    if (!c || n_polys < 0 || (n_polys > 0 && (!poly_offsets || !xy))) { fm_set_error("bad mask arguments"); return FM_EINVAL; }
+    if (stream >= c->S) { fm_set_error("stream %d out of range", stream); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    int npts = n_polys ? poly_offsets[n_polys] : 0;
+    std::vector<int> pts((size_t)npts * 2);
+    const double scale = c->info.scale;
+    for (int i = 0; i < npts * 2; i++) pts[i] = (int)((double)xy[i] * scale);   // find_motion.py:616 int(a*scale)
+    int s0 = stream < 0 ? 0 : stream, s1 = stream < 0 ? c->S : stream + 1;
+    for (int s = s0; s < s1; s++) {
+        int rc = fm_launch_masks(c, s, n_polys, poly_offsets, pts.data(), npts, 0);
+        if (rc) return rc;
+    }
+    FM_CUDA(cudaDeviceSynchronize());
+    return FM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// the hot path
+// --------------------------------------------------------------------------------------------
+extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
+                          int n_frames, void *cuda_stream, fm_frame_stats *stats_dev) {
+    if (!c || !frames) { fm_set_error("null argument"); return FM_EINVAL; }
+    if (n_frames < 1 || n_frames > c->Tmax) {
+        fm_set_error("n_frames %d outside [1, max_frames=%d]", n_frames, c->Tmax);
+        return FM_EINVAL;
+    }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    const bool fused = false;
+    if (c->timing) FM_CUDA(cudaEventRecord(c->ev[0], st));
+    if (fused) {
+        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
+        if (c->timing) { FM_CUDA(cudaEventRecord(c->ev[1], st)); FM_CUDA(cudaEventRecord(c->ev[2], st)); }
+    } else {
+        if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
+        if (c->timing) FM_CUDA(cudaEventRecord(c->ev[1], st));
+        if ((rc = fm_launch_temporal(c, n_frames, st))) return rc;
+        if (c->timing) FM_CUDA(cudaEventRecord(c->ev[2], st));
+    }
+    if ((rc = fm_launch_morph_ccl(c, n_frames, st, stats_dev))) return rc;
+    if (c->timing) {
+        FM_CUDA(cudaEventRecord(c->ev[3], st));
+        FM_CUDA(cudaEventSynchronize(c->ev[3]));
+        for (int i = 0; i < 3; i++) {
+            float ms = 0;
+            FM_CUDA(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+            c->t_ms[i] += ms;
+        }
+        c->t_calls++;
+    }
+    c->last_T = n_frames;
+    c->planes_valid = true;
+    return FM_OK;
+}
+
+extern "C" int fm_process_host(fm_ctx *c, const uint8_t *frames_host, size_t stream_stride, size_t frame_stride,
+                               int n_frames, fm_frame_stats *stats_host) {
+    if (!c || !frames_host || !stats_host) { fm_set_error("null argument"); return FM_EINVAL; }
+    if (n_frames < 1 || n_frames > c->Tmax) {
+        fm_set_error("n_frames %d outside [1, max_frames=%d]", n_frames, c->Tmax);
+        return FM_EINVAL;
+    }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t fb = (size_t)c->W * c->H * 3;
+    const size_t need = (size_t)c->S * n_frames * fb;
+    if (c->stage_bytes < need) {
+        cudaFree(c->stage_dev);
+        c->stage_dev = nullptr; c->stage_bytes = 0;
+        FM_CUDA(cudaMalloc(&c->stage_dev, need));
+        c->stage_bytes = need;
+    }
+    if (!c->stats_pinned) FM_CUDA(cudaMallocHost(&c->stats_pinned, (size_t)c->S * c->Tmax * sizeof(fm_frame_stats)));
+    cudaStream_t st = c->own_stream;
+    // densely packed device copy: [stream][frame][H][W][3]
+    if (frame_stride == fb && stream_stride == fb * (size_t)n_frames) {
+        FM_CUDA(cudaMemcpyAsync(c->stage_dev, frames_host, need, cudaMemcpyHostToDevice, st));
+    } else if (frame_stride == fb) {
+        for (int s = 0; s < c->S; s++)
+            FM_CUDA(cudaMemcpyAsync(c->stage_dev + (size_t)s * n_frames * fb, frames_host + s * stream_stride,
+                                    (size_t)n_frames * fb, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int s = 0; s < c->S; s++)
+            FM_CUDA(cudaMemcpy2DAsync(c->stage_dev + (size_t)s * n_frames * fb, fb, frames_host + s * stream_stride,
+                                      frame_stride, fb, n_frames, cudaMemcpyHostToDevice, st));
+    }
+    int rc = fm_process(c, c->stage_dev, fb * (size_t)n_frames, fb, n_frames, st, nullptr);
+    if (rc) return rc;
+    const size_t sb = (size_t)c->S * n_frames * sizeof(fm_frame_stats);
+    FM_CUDA(cudaMemcpyAsync(c->stats_pinned, c->stats, sb, cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    FM_CUDA(cudaMemcpyAsync(&err, c->errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaStreamSynchronize(st));
+    if (err) { fm_set_error("contour stage: run capacity exceeded"); return FM_ERANGE; }
+    memcpy(stats_host, c->stats_pinned, sb);
+    return FM_OK;
+}
+
+extern "C" int fm_get_components(fm_ctx *c, int stream, int t, int max_n, fm_component *out, int *n) {
+    if (!c || !n || (max_n > 0 && !out)) { fm_set_error("null argument"); return FM_EINVAL; }
+    if (!c->planes_valid || stream < 0 || stream >= c->S || t < 0 || t >= c->last_T) {
+        fm_set_error("no such frame in the last call");
+        return FM_EINVAL;
+    }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaDeviceSynchronize());
+    size_t f = (size_t)stream * c->last_T + t;
+    int cnt = 0;
+    FM_CUDA(cudaMemcpy(&cnt, c->ncomp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    int m = std::min(cnt, c->maxc);
+    std::vector<fm_component> v(m);
+    if (m) FM_CUDA(cudaMemcpy(v.data(), c->comps + f * c->maxc, (size_t)m * sizeof(fm_component), cudaMemcpyDeviceToHost));
+    std::sort(v.begin(), v.end(), [](const fm_component &a, const fm_component &b) {
+        if (a.area_x2 != b.area_x2) return a.area_x2 < b.area_x2;
+        if (a.x != b.x) return a.x < b.x;
+        if (a.y != b.y) return a.y < b.y;
+        if (a.w != b.w) return a.w < b.w;
+        return a.h < b.h;
+    });
+    for (int i = 0; i < std::min(m, max_n); i++) out[i] = v[i];
+    return FM_OK;
+}
+
+extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint8_t *blur, uint8_t *thresh,
+                               double *bg) {
+    if (!c) { fm_set_error("null context"); return FM_EINVAL; }
+    if (!c->planes_valid || stream < 0 || stream >= c->S || t < 0 || t >= c->last_T) {
+        fm_set_error("no such frame in the last call");
+        return FM_EINVAL;
+    }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaDeviceSynchronize());
+    size_t f = (size_t)stream * c->last_T + t;
+    if (gray) FM_CUDA(cudaMemcpy(gray, c->gray + f * c->N, c->N, cudaMemcpyDeviceToHost));
+    if (blur) FM_CUDA(cudaMemcpy(blur, c->blur + f * c->N, c->N, cudaMemcpyDeviceToHost));
+    if (thresh) {
+        uint8_t *d = nullptr;
+        FM_CUDA(cudaMalloc(&d, c->N));
+        int rc = fm_launch_thresh_export(c, stream, t, d, 0);
+        if (rc) return rc;
+        FM_CUDA(cudaMemcpy(thresh, d, c->N, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+    }
+    if (bg) {
+        double *d = nullptr;
+        FM_CUDA(cudaMalloc(&d, (size_t)c->N * sizeof(double)));
+        int rc = fm_launch_bg_export(c, stream, d, 0);
+        if (rc) return rc;
+        FM_CUDA(cudaMemcpy(bg, d, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+    }
+    return FM_OK;
+}
+
+extern "C" int fm_debug_mask(fm_ctx *c, int stream, uint8_t *mask) {
+    if (!c || !mask || stream < 0 || stream >= c->S) { fm_set_error("bad argument"); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    uint8_t *d = nullptr;
+    FM_CUDA(cudaMalloc(&d, c->N));
+    int rc = fm_launch_mask_export(c, stream, d, 0);
+    if (rc) return rc;
+    FM_CUDA(cudaMemcpy(mask, d, c->N, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return FM_OK;
+}
+
+extern "C" int fm_debug_components(int device, const uint8_t *plane, int w, int h, int max_n, fm_component *out,
+                                   int *n) {
+    if (!plane || !n || w < 1 || h < 1 || w > 65535) { fm_set_error("bad argument"); return FM_EINVAL; }
+    int ndev = 0;
+    FM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { fm_set_error("CUDA device %d not present", device); return FM_ECUDA; }
+    std::vector<fm_component> v(std::max(max_n, 1));
+    int rc = fm_ccl_plane(device, plane, w, h, max_n, v.data(), n);
+    if (rc) return rc;
+    int m = std::min(*n, max_n);
+    std::sort(v.begin(), v.begin() + m, [](const fm_component &a, const fm_component &b) {
+        if (a.area_x2 != b.area_x2) return a.area_x2 < b.area_x2;
+        if (a.x != b.x) return a.x < b.x;
+        if (a.y != b.y) return a.y < b.y;
+        if (a.w != b.w) return a.w < b.w;
+        return a.h < b.h;
+    });
+    for (int i = 0; i < m; i++) out[i] = v[i];
+    return FM_OK;
+}
+
+extern "C" int fm_timing_enable(fm_ctx *c, int on) {
+    if (!c) return FM_EINVAL;
+    c->timing = on != 0;
+    return FM_OK;
+}
+extern "C" int fm_timing_reset(fm_ctx *c) {
+    if (!c) return FM_EINVAL;
+    c->t_ms[0] = c->t_ms[1] = c->t_ms[2] = 0;
+    c->t_calls = 0;
+    return FM_OK;
+}
+extern "C" int fm_timing_get(fm_ctx *c, int which, double *ms_total, int64_t *n_calls) {
+    if (!c || which < 0 || which > 2) return FM_EINVAL;
+    if (ms_total) *ms_total = c->t_ms[which];
+    if (n_calls) *n_calls = c->t_calls;
+    return FM_OK;
+}
+
+int fm_launch_fused(fm_ctx *, const uint8_t *, size_t, size_t, int, cudaStream_t) {
+    fm_set_error("fused front end not built");
+    return FM_ERANGE;
+}

@@ -1,0 +1,500 @@
+// Dilation, external-contour extraction and the per-frame decision logic on bit planes.
+// Replaces VideoFrame.find_contours (cv2.dilate x2 + cv2.findContours RETR_EXTERNAL), the
+// cv2.contourArea / boundingRect calls of find_movement, and the counters of find_movement /
+// decide_output (find_motion/find_motion.py:260-276, 665-700, 549-589).
+//
+// Contours are obtained without border following:
+//   O  = background 4-connected to the outside of the image
+//   F  = not O  (foreground with its holes filled)
+//   external contours <-> 8-connected components of F
+//   contourArea = Q4 + Q3/2 over the 2x2 windows of the component (4 resp. 3 pixels set)
+// Both labellings are run-based union-find with one warp per row: lanes hold the 32-bit words
+// of the row, run starts/ends come from shifted-word logic and are enumerated with warp prefix
+// sums, unions are lock-free atomicMin links between runs of adjacent rows.
+#include "fm_common.cuh"
+
+#define WARPS_PER_BLOCK 8
+
+__device__ __forceinline__ uint32_t ld_word(const uint32_t *row, int j, int wpr) {
+    return ((unsigned)j < (unsigned)wpr) ? __ldg(row + j) : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dilate: flat raw threshold bits -> row-padded 5x5-dilated bit plane (+ any flag)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t flat_row_word(const uint32_t *flat, int y, int j, int w, int h, int wpr) {
+    // 32 pixels x = 32j .. 32j+31 of row y as a word (bits beyond w cleared)
+    if ((unsigned)y >= (unsigned)h || (unsigned)j >= (unsigned)wpr) return 0u;
+    long long b0 = (long long)y * w + 32 * j;
+    int wi = (int)(b0 >> 5), sh = (int)(b0 & 31);
+    uint32_t lo = __ldg(flat + wi);
+    uint32_t v = lo;
+    if (sh) {
+        uint32_t hi = __ldg(flat + wi + 1);      // flat planes are padded by one tile
+        v = __funnelshift_r(lo, hi, sh);
+    }
+    int rem = w - 32 * j;
+    if (rem < 32) v &= (1u << rem) - 1u;
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t *__restrict__ tflat,
+                                                                 uint32_t *__restrict__ dil, int *__restrict__ any,
+                                                                 int F, int w, int h, int wpr, int flatwords) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= F * h) return;
+    int f = warp / h, y = warp - f * h;
+    const uint32_t *flat = tflat + (size_t)f * flatwords;
+    uint32_t *out = dil + ((size_t)f * h + y) * wpr;
+    uint32_t anyw = 0;
+    for (int j = lane; j < wpr; j += 32) {
+        uint32_t vm = 0, vc = 0, vp = 0;    // vertical OR of words j-1, j, j+1
+#pragma unroll
+        for (int dy = -2; dy <= 2; dy++) {
+            vm |= flat_row_word(flat, y + dy, j - 1, w, h, wpr);
+            vc |= flat_row_word(flat, y + dy, j, w, h, wpr);
+            vp |= flat_row_word(flat, y + dy, j + 1, w, h, wpr);
+        }
+        uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) |
+                     (vp << 30);
+        int rem = w - 32 * j;
+        if (rem < 32) d &= (1u << rem) - 1u;
+        out[j] = d;
+        anyw |= d;
+    }
+    if (__any_sync(0xffffffffu, anyw != 0) && lane == 0) atomicOr(any + f, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// run extraction
+// ---------------------------------------------------------------------------------------------
+struct CclArgs {
+    const uint32_t *plane;     // [F][h][wpr] bit plane of this pass
+    const int *any;            // [F] skip frames without set pixels (may be NULL)
+    int f0, nf;                // frames [f0, f0+nf) of the call are in this sub-batch
+    int w, h, wpr, cap;
+    size_t slots;
+    uint16_t *xs, *xe;
+    int *rowcnt, *parent, *area2, *bbox;
+    int *errflag;
+};
+
+template <bool INVERT>
+__device__ __forceinline__ uint32_t plane_word(const uint32_t *row, int j, int w, int wpr) {
+    if ((unsigned)j >= (unsigned)wpr) return 0u;
+    uint32_t v = __ldg(row + j);
+    if (INVERT) {
+        v = ~v;
+        int rem = w - 32 * j;
+        if (rem < 32) v &= (1u << rem) - 1u;
+    }
+    return v;
+}
+
+template <bool INVERT>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_runs(CclArgs a) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= a.nf * a.h) return;
+    int lf = warp / a.h, y = warp - lf * a.h;
+    int f = a.f0 + lf;
+    if (a.any && !a.any[f]) return;
+    const uint32_t *row = a.plane + ((size_t)f * a.h + y) * a.wpr;
+    size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
+    int *parent = a.parent + (size_t)lf * (a.slots + 1);
+    if (y == 0 && lane == 0) parent[0] = 0;      // the outside node
+    int nstart = 0, nend = 0;
+    for (int j0 = 0; j0 < a.wpr; j0 += 32) {
+        int j = j0 + lane;
+        uint32_t B = plane_word<INVERT>(row, j, a.w, a.wpr);
+        uint32_t Bp = plane_word<INVERT>(row, j - 1, a.w, a.wpr);
+        uint32_t Bn = plane_word<INVERT>(row, j + 1, a.w, a.wpr);
+        uint32_t S = B & ~((B << 1) | (Bp >> 31));
+        uint32_t E = B & ~((B >> 1) | (Bn << 31));
+        int cs = __popc(S), ce = __popc(E);
+        int ps = cs, pe = ce;     // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int vs = __shfl_up_sync(0xffffffffu, ps, o);
+            int ve = __shfl_up_sync(0xffffffffu, pe, o);
+            if (lane >= o) { ps += vs; pe += ve; }
+        }
+        int is = nstart + ps - cs, ie = nend + pe - ce;
+        while (S) {
+            int bit = __ffs(S) - 1;
+            S &= S - 1;
+            if (is < a.cap) {
+                a.xs[base + is] = (uint16_t)(32 * j + bit);
+                parent[1 + (size_t)y * a.cap + is] = 1 + y * a.cap + is;
+                a.area2[base + is] = 0;
+                int *bb = a.bbox + (base + is) * 4;
+                bb[0] = 0x7fffffff; bb[1] = 0x7fffffff; bb[2] = -1; bb[3] = -1;
+            }
+            is++;
+        }
+        while (E) {
+            int bit = __ffs(E) - 1;
+            E &= E - 1;
+            if (ie < a.cap) a.xe[base + ie] = (uint16_t)(32 * j + bit);
+            ie++;
+        }
+        nstart += __shfl_sync(0xffffffffu, ps, 31);
+        nend += __shfl_sync(0xffffffffu, pe, 31);
+    }
+    if (lane == 0) {
+        if (nstart > a.cap) { atomicExch(a.errflag, 1); nstart = a.cap; }
+        a.rowcnt[(size_t)lf * a.h + y] = nstart;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// union-find on run ids (id 0 = outside, run (y, i) = 1 + y*cap + i); roots are minimal ids
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// CONN8: runs of adjacent rows touch if their x ranges overlap after growing by one pixel.
+// OUTSIDE: runs that touch the image border are linked to the outside node (background pass).
+template <bool CONN8, bool OUTSIDE>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_union(CclArgs a) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= a.nf * a.h) return;
+    int lf = warp / a.h, y = warp - lf * a.h;
+    int f = a.f0 + lf;
+    if (a.any && !a.any[f]) return;
+    int n = a.rowcnt[(size_t)lf * a.h + y];
+    if (n == 0) return;
+    size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
+    int *parent = a.parent + (size_t)lf * (a.slots + 1);
+    int np = y > 0 ? a.rowcnt[(size_t)lf * a.h + y - 1] : 0;
+    const uint16_t *pxs = a.xs + base - a.cap, *pxe = a.xe + base - a.cap;
+    const int d = CONN8 ? 1 : 0;
+    for (int i = lane; i < n; i += 32) {
+        int xs = a.xs[base + i], xe = a.xe[base + i];
+        int id = 1 + y * a.cap + i;
+        if (OUTSIDE && (y == 0 || y == a.h - 1 || xs == 0 || xe == a.w - 1)) uf_union(parent, id, 0);
+        if (np) {
+            // first run of the previous row whose end reaches xs - d
+            int lo = 0, hi = np;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)pxe[mid] < xs - d) lo = mid + 1; else hi = mid;
+            }
+            for (int q = lo; q < np && (int)pxs[q] <= xe + d; q++) uf_union(parent, id, 1 + (y - 1) * a.cap + q);
+        }
+    }
+}
+
+// background pass epilogue: F = plane | (background runs not connected to the outside)
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_fill_holes(CclArgs a, uint32_t *__restrict__ fill) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= a.nf * a.h) return;
+    int lf = warp / a.h, y = warp - lf * a.h;
+    int f = a.f0 + lf;
+    if (a.any && !a.any[f]) return;
+    const uint32_t *row = a.plane + ((size_t)f * a.h + y) * a.wpr;
+    uint32_t *out = fill + ((size_t)f * a.h + y) * a.wpr;
+    for (int j = lane; j < a.wpr; j += 32) out[j] = row[j];
+    __syncwarp();
+    int n = a.rowcnt[(size_t)lf * a.h + y];
+    size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
+    const int *parent = a.parent + (size_t)lf * (a.slots + 1);
+    for (int i = lane; i < n; i += 32) {
+        if (uf_find(parent, 1 + y * a.cap + i) == 0) continue;
+        int xs = a.xs[base + i], xe = a.xe[base + i];
+        for (int j = xs >> 5; j <= (xe >> 5); j++) {
+            int lo = max(xs - 32 * j, 0), hi = min(xe - 32 * j, 31);
+            uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(out + j, m);
+        }
+    }
+}
+
+// per run: bit-quad area contribution (windows whose lower row is y) and bounding box -> root
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_run_stats(CclArgs a) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= a.nf * a.h) return;
+    int lf = warp / a.h, y = warp - lf * a.h;
+    int f = a.f0 + lf;
+    if (a.any && !a.any[f]) return;
+    int n = a.rowcnt[(size_t)lf * a.h + y];
+    if (n == 0) return;
+    size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
+    const int *parent = a.parent + (size_t)lf * (a.slots + 1);
+    const uint32_t *up = a.plane + ((size_t)f * a.h + y - 1) * a.wpr;   // row y-1 (unused for y == 0)
+    for (int i = lane; i < n; i += 32) {
+        int xs = a.xs[base + i], xe = a.xe[base + i];
+        int root = uf_find(parent, 1 + y * a.cap + i) - 1;
+        int q = 0;
+        if (y > 0) {
+            // windows x in [xs, xe-1] have both lower pixels set: count upper pairs
+            if (xe > xs) {
+                int x0 = xs, x1 = xe - 1;
+                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
+                    uint32_t U = ld_word(up, j, a.wpr), Un = ld_word(up, j + 1, a.wpr);
+                    uint32_t Us = (U >> 1) | (Un << 31);            // bit i = pixel x+1
+                    int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
+                    uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    q += 2 * __popc(U & Us & m) + __popc((U ^ Us) & m);
+                }
+            }
+            // windows x = xs-1 (lower 0,1) and x = xe (lower 1,0): need both upper pixels
+            auto ubit = [&](int x) -> uint32_t {
+                if (x < 0 || x >= a.w) return 0u;
+                return (__ldg(up + (x >> 5)) >> (x & 31)) & 1u;
+            };
+            q += (int)(ubit(xs - 1) & ubit(xs)) + (int)(ubit(xe) & ubit(xe + 1));
+        }
+        size_t r = (size_t)lf * a.slots + root;
+        if (q) atomicAdd(a.area2 + r, q);
+        int *bb = a.bbox + r * 4;
+        atomicMin(bb + 0, xs);
+        atomicMin(bb + 1, y);
+        atomicMax(bb + 2, xe);
+        atomicMax(bb + 3, y);
+    }
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_collect(CclArgs a, int *__restrict__ ncomp,
+                                                                  int *__restrict__ ncounted,
+                                                                  fm_component *__restrict__ comps, int maxc,
+                                                                  int min_area, int max_area) {
+    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= a.nf * a.h) return;
+    int lf = warp / a.h, y = warp - lf * a.h;
+    int f = a.f0 + lf;
+    if (a.any && !a.any[f]) return;
+    int n = a.rowcnt[(size_t)lf * a.h + y];
+    size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
+    const int *parent = a.parent + (size_t)lf * (a.slots + 1);
+    for (int i = lane; i < n; i += 32) {
+        int id = 1 + y * a.cap + i;
+        if (__ldcg(parent + id) != id) continue;
+        int area2 = a.area2[base + i];
+        const int *bb = a.bbox + (base + i) * 4;
+        int slot = atomicAdd(ncomp + f, 1);
+        // find_motion.py:684  `if self.max_area < area < self.min_area: continue`  (area = area2/2)
+        bool skipped = (2LL * max_area < area2) && (area2 < 2LL * min_area);
+        if (!skipped) atomicAdd(ncounted + f, 1);
+        if (slot < maxc) {
+            fm_component c;
+            c.area_x2 = area2;
+            c.x = bb[0]; c.y = bb[1]; c.w = bb[2] - bb[0] + 1; c.h = bb[3] - bb[1] + 1;
+            comps[(size_t)f * maxc + slot] = c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decision state machine, one thread per stream, frames in order
+// ---------------------------------------------------------------------------------------------
+__global__ void k_decide(StreamState *__restrict__ state, const int *__restrict__ ncomp,
+                         const int *__restrict__ ncounted, fm_frame_stats *__restrict__ stats,
+                         fm_frame_stats *__restrict__ stats_out, int S, int T, int cache_frames,
+                         int min_movement_frames) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    StreamState st = state[s];
+    for (int t = 0; t < T; t++) {
+        int f = s * T + t;
+        fm_frame_stats r;
+        r.n_contours = ncomp[f];
+        r.n_counted = ncounted[f];
+        if (st.decay > 0) st.decay -= 1;                       // find_motion.py:672
+        bool movement = r.n_counted > 0;
+        st.counter = movement ? st.counter + r.n_counted : 0;   // :694 per contour, :697-698
+        r.wrote = 0;
+        r.n_flush = 0;
+        if (st.counter >= min_movement_frames || st.decay > 0) {   // :555
+            if (movement) {
+                st.decay = cache_frames;                        // :559
+                r.n_flush = st.cache_len;                       // :561-570
+                st.cache_len = 0;
+            }
+            r.wrote = 1;                                        // :583
+        } else {
+            st.cache_len = min(st.cache_len + 1, cache_frames); // deque(maxlen), :415, :588
+        }
+        r.movement = movement ? 1 : 0;
+        r.movement_counter = st.counter;
+        r.movement_decay = st.decay;
+        r.cache_len = st.cache_len;
+        stats[f] = r;
+        if (stats_out) stats_out[f] = r;
+    }
+    st.has_bg = 1;
+    state[s] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exports for the parity tests
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bits_to_u8(const uint32_t *__restrict__ plane, uint8_t *__restrict__ dst, int w, int h, int wpr,
+                             uint8_t on) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    dst[(size_t)y * w + x] = ((plane[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? on : 0;
+}
+
+__global__ void k_u8_to_bits(const uint8_t *__restrict__ src, uint32_t *__restrict__ plane, int w, int h, int wpr) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (j >= wpr) return;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; b++) {
+        int x = 32 * j + b;
+        if (x < w && src[(size_t)y * w + x]) v |= 1u << b;
+    }
+    plane[(size_t)y * wpr + j] = v;
+}
+
+int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st) {
+    const uint32_t *pl = c->dil + ((size_t)stream * c->last_T + t) * c->h * c->wpr;
+    dim3 grid((c->w + 127) / 128, c->h);
+    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 255);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st) {
+    const uint32_t *pl = c->maskbits + (size_t)stream * c->h * c->wpr;
+    dim3 grid((c->w + 127) / 128, c->h);
+    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 1);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap) {
+    s->frames = frames;
+    s->cap = cap;
+    s->slots = (size_t)h * cap;
+    size_t n = (size_t)frames * s->slots;
+    FM_CUDA(cudaMalloc(&s->xs, n * sizeof(uint16_t)));
+    FM_CUDA(cudaMalloc(&s->xe, n * sizeof(uint16_t)));
+    FM_CUDA(cudaMalloc(&s->rowcnt, (size_t)frames * h * sizeof(int)));
+    FM_CUDA(cudaMalloc(&s->parent, (size_t)frames * (s->slots + 1) * sizeof(int)));
+    FM_CUDA(cudaMalloc(&s->area2, n * sizeof(int)));
+    FM_CUDA(cudaMalloc(&s->bbox, n * 4 * sizeof(int)));
+    return FM_OK;
+}
+
+void fm_ccl_free(CclScratch *s) {
+    cudaFree(s->xs); cudaFree(s->xe); cudaFree(s->rowcnt); cudaFree(s->parent); cudaFree(s->area2);
+    cudaFree(s->bbox);
+    s->xs = s->xe = nullptr; s->rowcnt = s->parent = s->area2 = s->bbox = nullptr;
+}
+
+// labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
+static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *any, int F, int w,
+                   int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
+                   int max_area, int *errflag, cudaStream_t st) {
+    for (int f0 = 0; f0 < F; f0 += sc.frames) {
+        int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
+        CclArgs a;
+        a.any = any; a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
+        a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
+        a.bbox = sc.bbox; a.errflag = errflag;
+        int blocks = (nf * h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        int thr = 32 * WARPS_PER_BLOCK;
+        // pass 1: background, 4-connected, linked to the outside -> holes
+        a.plane = plane;
+        k_runs<true><<<blocks, thr, 0, st>>>(a);
+        FM_LAUNCH_CHECK();
+        k_union<false, true><<<blocks, thr, 0, st>>>(a);
+        FM_LAUNCH_CHECK();
+        k_fill_holes<<<blocks, thr, 0, st>>>(a, fill);
+        FM_LAUNCH_CHECK();
+        // pass 2: hole-filled foreground, 8-connected
+        a.plane = fill;
+        k_runs<false><<<blocks, thr, 0, st>>>(a);
+        FM_LAUNCH_CHECK();
+        k_union<true, false><<<blocks, thr, 0, st>>>(a);
+        FM_LAUNCH_CHECK();
+        k_run_stats<<<blocks, thr, 0, st>>>(a);
+        FM_LAUNCH_CHECK();
+        k_collect<<<blocks, thr, 0, st>>>(a, ncomp, ncounted, comps, maxc, min_area, max_area);
+        FM_LAUNCH_CHECK();
+    }
+    return FM_OK;
+}
+
+int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
+    const int F = c->S * T;
+    FM_CUDA(cudaMemsetAsync(c->any, 0, (size_t)F * sizeof(int), st));
+    FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (size_t)F * sizeof(int), st));
+    FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
+    int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    k_dilate<<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, F, c->w, c->h, c->wpr,
+                                                     c->ntiles * FM_TILE_WORDS);
+    FM_LAUNCH_CHECK();
+    int rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
+                     c->maxc, c->info.min_area, c->info.max_area, c->errflag, st);
+    if (rc) return rc;
+    k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(c->state, c->ncomp, c->ncounted, c->stats, stats_out, c->S, T,
+                                                 c->info.cache_frames, c->info.min_movement_frames);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+// standalone labelling of one host plane (parity tests of the contour stage)
+int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out, int *n) {
+    FM_CUDA(cudaSetDevice(device));
+    int wpr = (w + 31) / 32;
+    CclScratch sc{};
+    int rc = fm_ccl_alloc(&sc, 1, h, w / 2 + 2);
+    if (rc) return rc;
+    uint8_t *d8 = nullptr;
+    uint32_t *pl = nullptr, *fill = nullptr;
+    int *cnt = nullptr;
+    fm_component *comps = nullptr;
+    int maxc = max_n > 0 ? max_n : 1;
+    FM_CUDA(cudaMalloc(&d8, (size_t)w * h));
+    FM_CUDA(cudaMalloc(&pl, (size_t)wpr * h * 4));
+    FM_CUDA(cudaMalloc(&fill, (size_t)wpr * h * 4));
+    FM_CUDA(cudaMalloc(&cnt, 3 * sizeof(int)));
+    FM_CUDA(cudaMalloc(&comps, (size_t)maxc * sizeof(fm_component)));
+    FM_CUDA(cudaMemcpy(d8, plane_host, (size_t)w * h, cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMemset(cnt, 0, 3 * sizeof(int)));
+    dim3 grid((wpr + 63) / 64, h);
+    k_u8_to_bits<<<grid, 64>>>(d8, pl, w, h, wpr);
+    FM_LAUNCH_CHECK();
+    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, 0);
+    if (rc) return rc;
+    int hc[3];
+    FM_CUDA(cudaMemcpy(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (hc[2]) {
+        fm_set_error("contour stage: run capacity exceeded");
+        return FM_ERANGE;
+    }
+    *n = hc[0];
+    int m = hc[0] < maxc ? hc[0] : maxc;
+    if (max_n > 0 && m > 0) FM_CUDA(cudaMemcpy(out, comps, (size_t)m * sizeof(fm_component), cudaMemcpyDeviceToHost));
+    cudaFree(d8); cudaFree(pl); cudaFree(fill); cudaFree(cnt); cudaFree(comps);
+    fm_ccl_free(&sc);
+    return FM_OK;
+}

@@ -1,0 +1,167 @@
+"""MotionEngine: thin Python handle on an fm_ctx (include/fm_gpu.h).
+
+One engine = n_streams streams of equal geometry and tuning processed as a batch on one GPU,
+the B200 replacement of one `partial(run_vid, **tuning)` job set (find_motion.py:1323-1331).
+torch is used only for device memory, streams and pinned host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+STATS_DTYPE = np.dtype([(n, np.int32) for n in ("n_contours", "n_counted", "movement", "movement_counter",
+                                                "movement_decay", "cache_len", "wrote", "n_flush")])
+
+
+class MotionEngine:
+    def __init__(self, frame_width, frame_height, n_streams=1, max_frames=8, device=0, fps=30, box_size=100,
+                 min_box_scale=50, cache_time=2.0, min_time=0.5, threshold=7, avg=0.1, blur_scale=20,
+                 mask_areas=None, max_components=256, keep_planes=False, no_fused=False):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        cfg = _lib.fm_config(
+            device=device, n_streams=n_streams, frame_width=frame_width, frame_height=frame_height,
+            max_frames=max_frames, fps=int(fps), box_size=int(box_size), min_box_scale=int(min_box_scale),
+            blur_scale=int(blur_scale), threshold=int(threshold), avg=float(avg), min_time=float(min_time),
+            cache_time=float(cache_time), max_components=max_components,
+            flags=(_lib.FLAG_KEEP_PLANES if keep_planes else 0) | (_lib.FLAG_NO_FUSED if no_fused else 0))
+        _lib.check(self._lib.fm_ctx_create(C.byref(cfg), C.byref(self._ctx)))
+        self.device = device
+        self.n_streams, self.max_frames = n_streams, max_frames
+        self.W, self.H = frame_width, frame_height
+        inf = _lib.fm_info()
+        _lib.check(self._lib.fm_ctx_info(self._ctx, C.byref(inf)))
+        self.info = {f: getattr(inf, f) for f, _ in _lib.fm_info._fields_ if f != "reserved"}
+        self.w, self.h = inf.proc_width, inf.proc_height
+        self._stats_dev = None
+        if mask_areas:
+            self.set_masks(mask_areas)
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.fm_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration --------------------------------------------------------------------------
+    def set_masks(self, mask_areas, stream=-1):
+        """mask_areas: the reference's list of areas, each a tuple of (x, y) points in SOURCE
+        pixels; two points = rectangle, more = polygon (find_motion.py:619-635)."""
+        offs, xy = [0], []
+        for area in mask_areas or []:
+            for (x, y) in area:
+                xy += [int(x), int(y)]
+            offs.append(len(xy) // 2)
+        n = len(offs) - 1
+        offs_a = (C.c_int32 * len(offs))(*offs)
+        xy_a = (C.c_int32 * max(len(xy), 1))(*xy)
+        _lib.check(self._lib.fm_ctx_set_masks(self._ctx, stream, n, offs_a, xy_a))
+
+    def reset(self, stream=-1):
+        _lib.check(self._lib.fm_ctx_reset(self._ctx, stream))
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def process(self, frames, sync=True):
+        """frames: CUDA uint8 tensor [n_streams, T, H, W, 3] (BGR).  Returns the per-frame stats
+        as a structured numpy array [n_streams, T] (or the device tensor if sync=False)."""
+        import torch
+
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5, "uint8 CUDA [S,T,H,W,3]"
+        S, T, H, W, ch = frames.shape
+        assert (S, H, W, ch) == (self.n_streams, self.H, self.W, 3), "frame geometry mismatch"
+        assert frames[0, 0].is_contiguous()
+        need = S * T * STATS_DTYPE.itemsize
+        if self._stats_dev is None or self._stats_dev.numel() < need:
+            self._stats_dev = torch.empty(S * self.max_frames * STATS_DTYPE.itemsize, dtype=torch.uint8,
+                                          device=frames.device)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        _lib.check(self._lib.fm_process(self._ctx, frames.data_ptr(), frames.stride(0), frames.stride(1), T,
+                                        C.c_void_p(st), self._stats_dev.data_ptr()))
+        if not sync:
+            return self._stats_dev[:need]
+        host = self._stats_dev[:need].cpu().numpy()
+        return host.view(STATS_DTYPE).reshape(S, T)
+
+    def process_host(self, frames):
+        """frames: host uint8 array / pinned tensor [n_streams, T, H, W, 3].  Copies in, runs,
+        copies the stats out (the end-to-end call of the drop-in adapter)."""
+        if hasattr(frames, "data_ptr"):
+            ptr, shape = frames.data_ptr(), tuple(frames.shape)
+            s0, s1 = frames.stride(0), frames.stride(1)
+        else:
+            frames = np.ascontiguousarray(frames)
+            ptr, shape = frames.ctypes.data, frames.shape
+            s0, s1 = frames.strides[0], frames.strides[1]
+        S, T, H, W, ch = shape
+        assert (S, H, W, ch) == (self.n_streams, self.H, self.W, 3), "frame geometry mismatch"
+        out = np.empty((S, T), STATS_DTYPE)
+        _lib.check(self._lib.fm_process_host(self._ctx, C.c_void_p(ptr), s0, s1, T, C.c_void_p(out.ctypes.data)))
+        return out
+
+    # -- taps ---------------------------------------------------------------------------------------
+    def components(self, stream, t, max_n=None):
+        max_n = max_n or 4096
+        buf = (_lib.fm_component * max_n)()
+        n = C.c_int(0)
+        _lib.check(self._lib.fm_get_components(self._ctx, stream, t, max_n, buf, C.byref(n)))
+        m = min(n.value, max_n)
+        return n.value, [(buf[i].area_x2, (buf[i].x, buf[i].y, buf[i].w, buf[i].h)) for i in range(m)]
+
+    def planes(self, stream, t, gray=True, blur=True, thresh=True, bg=True):
+        out = {}
+        arrs = {}
+        for key, want, dt in (("gray", gray, np.uint8), ("blur", blur, np.uint8), ("thresh", thresh, np.uint8),
+                              ("bg", bg, np.float64)):
+            arrs[key] = np.empty((self.h, self.w), dt) if want else None
+        ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        _lib.check(self._lib.fm_debug_planes(self._ctx, stream, t, ptr(arrs["gray"]), ptr(arrs["blur"]),
+                                             ptr(arrs["thresh"]), ptr(arrs["bg"])))
+        out.update({k: v for k, v in arrs.items() if v is not None})
+        return out
+
+    def mask(self, stream=0):
+        m = np.empty((self.h, self.w), np.uint8)
+        _lib.check(self._lib.fm_debug_mask(self._ctx, stream, C.c_void_p(m.ctypes.data)))
+        return m
+
+    def timing(self, enable=None, reset=False):
+        if enable is not None:
+            _lib.check(self._lib.fm_timing_enable(self._ctx, int(enable)))
+        if reset:
+            _lib.check(self._lib.fm_timing_reset(self._ctx))
+        res = {}
+        for i, name in enumerate(("front_end", "temporal", "contours")):
+            ms, n = C.c_double(0), C.c_int64(0)
+            _lib.check(self._lib.fm_timing_get(self._ctx, i, C.byref(ms), C.byref(n)))
+            res[name] = (ms.value, n.value)
+        return res
+
+
+def label_components(plane: np.ndarray, device=0, max_n=65536):
+    """findContours(RETR_EXTERNAL)+contourArea+boundingRect of a host uint8 plane on the GPU."""
+    lib = _lib.load()
+    plane = np.ascontiguousarray(plane, np.uint8)
+    h, w = plane.shape
+    buf = (_lib.fm_component * max_n)()
+    n = C.c_int(0)
+    _lib.check(lib.fm_debug_components(device, C.c_void_p(plane.ctypes.data), w, h, max_n, buf, C.byref(n)))
+    return [(buf[i].area_x2, (buf[i].x, buf[i].y, buf[i].w, buf[i].h)) for i in range(min(n.value, max_n))]
+
+
+def launch_count() -> int:
+    return int(_lib.load().fm_launch_count())

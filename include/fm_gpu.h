@@ -1,0 +1,158 @@
+/*
+ * fm_gpu.h -- C ABI of libfmgpu.so, the B200 (sm_100a) implementation of find_motion's
+ * per-frame motion-detection hot path.
+ *
+ * The reference (dmiruke/find_motion) has no FFI of its own: its hot path is the cv2 call chain
+ * inside VideoMotion (find_motion/find_motion.py:487-494 blur_frame, :619-635 mask_off_areas,
+ * :638-662 find_diff, :246-276 VideoFrame.diff/threshold/find_contours, :665-700 find_movement,
+ * :549-589 decide_output) driven by the per-stream loop VideoMotion.find_motion (:852-904) and
+ * fanned out one process per stream by run_pool/run_map/run_stream (:1054-1210).  This header
+ * is the boundary a maintainer binds instead of those calls (ctypes stub: INTEGRATION.md).
+ *
+ * Conventions: every entry point returns 0 on success or a negative FM_E* code;
+ * fm_last_error() returns a thread-local message.  A context is not thread-safe; distinct
+ * contexts are independent.  One context = n_streams streams of identical geometry and tuning
+ * (what `partial(run_vid, **tuning)` gives every job, find_motion.py:1323-1331), processed as a
+ * batch.  There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FM_GPU_H
+#define FM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_OK 0
+#define FM_EINVAL (-1)   /* bad argument */
+#define FM_ECUDA (-2)    /* CUDA runtime error (text in fm_last_error) */
+#define FM_ENOMEM (-3)
+#define FM_ERANGE (-4)   /* configuration outside the supported range */
+
+typedef struct fm_ctx fm_ctx;
+
+/* Tuning options: names, meaning and defaults of VideoMotion.__init__ (find_motion.py:299-307)
+ * plus the geometry that _load_video reads from the capture (find_motion.py:413-423). */
+typedef struct fm_config {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t n_streams;       /* streams batched in this context */
+    int32_t frame_width;     /* W of the raw BGR frames (CAP_PROP_FRAME_WIDTH) */
+    int32_t frame_height;    /* H */
+    int32_t max_frames;      /* most frames per stream a single fm_process call will carry (T_max) */
+    int32_t fps;             /* --fps, default 30 (find_motion.py:1463) */
+    int32_t box_size;        /* --box-size, default 100: processing width (find_motion.py:492) */
+    int32_t min_box_scale;   /* --min-box-scale, default 50 (find_motion.py:406) */
+    int32_t blur_scale;      /* --blur-scale, default 20 (find_motion.py:482-484) */
+    int32_t threshold;       /* --threshold, CLI default 12 / ctor default 7 (find_motion.py:257) */
+    double avg;              /* --avg, default 0.1 (find_motion.py:659) */
+    double min_time;         /* --mintime, default 0.5 s (find_motion.py:335) */
+    double cache_time;       /* --cachetime, CLI default 1.0 / ctor default 2.0 (find_motion.py:334) */
+    int32_t max_components;  /* per-frame component records kept for fm_get_components (0 -> 256) */
+    int32_t flags;           /* FM_FLAG_* */
+} fm_config;
+
+#define FM_FLAG_KEEP_PLANES 1   /* keep gray/blur planes of the last call for fm_debug_planes */
+#define FM_FLAG_NO_FUSED    2   /* force the generic multi-kernel front end (A/B testing) */
+
+/* Derived parameters, exactly as the reference computes them. */
+typedef struct fm_info {
+    int32_t proc_width;            /* w = box_size */
+    int32_t proc_height;           /* h = int(H * (box_size / float(W)))  (imutils.resize) */
+    int32_t gaussian;              /* odd(int(box_size / blur_scale)) */
+    int32_t min_area;              /* int((box_size / min_box_scale) ** 2) */
+    int32_t max_area;              /* int(W * H / 2 * scale) */
+    int32_t cache_frames;          /* int(cache_time * fps) */
+    int32_t min_movement_frames;   /* int(min_time * fps) */
+    int32_t words_per_row;         /* 32-bit words per row of the bit planes */
+    double scale;                  /* box_size / frame_width */
+    int32_t front_end;             /* 0 = fused full-res stencil, 1 = generic blur, 2 = resize front end */
+    int32_t reserved;
+} fm_info;
+
+/* Per-frame result: everything find_movement + decide_output decide (find_motion.py:665-700,
+ * 549-589), in frame order.  The host adapter replays `wrote` / `n_flush` on the raw frames. */
+typedef struct fm_frame_stats {
+    int32_t n_contours;         /* len(frame.contours): external contours of the dilated mask */
+    int32_t n_counted;          /* contours not skipped by `max_area < area < min_area` (:684) */
+    int32_t movement;           /* self.movement after find_movement */
+    int32_t movement_counter;   /* self.movement_counter after find_movement (per CONTOUR, :694) */
+    int32_t movement_decay;     /* self.movement_decay after decide_output */
+    int32_t cache_len;          /* len(self.frame_cache) after decide_output */
+    int32_t wrote;              /* 1 if output_frame() ran for this frame (:583) */
+    int32_t n_flush;            /* cached raw frames written before it (:561-570) */
+} fm_frame_stats;
+
+/* One external contour: 2*cv2.contourArea (an integer) and cv2.boundingRect (find_motion.py:679, 792). */
+typedef struct fm_component {
+    int32_t area_x2;
+    int32_t x, y, w, h;
+} fm_component;
+
+const char *fm_last_error(void);
+int fm_version(void);
+
+/* Replaces VideoMotion.__init__ + _calc_min_area + _make_gaussian + _load_video
+ * (find_motion.py:299-380, 402-424, 478-484) for n_streams streams. */
+int fm_ctx_create(const fm_config *cfg, fm_ctx **out);
+int fm_ctx_destroy(fm_ctx *ctx);
+int fm_ctx_info(const fm_ctx *ctx, fm_info *info);
+
+/* Replaces mask_off_areas' per-frame drawing (find_motion.py:619-635): the polygons are
+ * rasterised once on the device with cv2.rectangle(FILLED) / cv2.fillConvexPoly semantics.
+ * xy holds the user's UNSCALED integer coordinates (x0,y0,x1,y1,...); poly_offsets[i] ..
+ * poly_offsets[i+1] index the points of polygon i (2 points = rectangle).  stream < 0 = all. */
+int fm_ctx_set_masks(fm_ctx *ctx, int stream, int n_polys, const int32_t *poly_offsets,
+                     const int32_t *xy);
+
+/* ref_frame = None, counters = 0, frame cache emptied (find_motion.py:362-371, 414-415). */
+int fm_ctx_reset(fm_ctx *ctx, int stream);
+
+/* The hot path: for every stream s < n_streams and t < n_frames (in order), run
+ * blur_frame -> mask_off_areas -> find_diff -> find_movement -> decide_output on the BGR frame
+ *   frames + s * stream_stride + t * frame_stride          (H*W*3 bytes, HWC, uint8)
+ * `frames` is a DEVICE pointer; work is enqueued on `cuda_stream` (a cudaStream_t, 0 = default)
+ * and the call returns without synchronising.  stats_dev, if not NULL, is a device buffer of
+ * n_streams * n_frames fm_frame_stats ([stream][frame]) filled by the call. */
+int fm_process(fm_ctx *ctx, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
+               int n_frames, void *cuda_stream, fm_frame_stats *stats_dev);
+
+/* Same with HOST buffers: copies the frames host->device (pinned memory recommended), runs the
+ * path, copies the stats back and synchronises.  This is the call a drop-in adapter makes. */
+int fm_process_host(fm_ctx *ctx, const uint8_t *frames_host, size_t stream_stride,
+                    size_t frame_stride, int n_frames, fm_frame_stats *stats_host);
+
+/* Components (contours) of frame t of the LAST fm_process call, sorted by (area_x2, x, y, w, h).
+ * Writes min(n, max_n) records and the true count to *n.  Synchronises. */
+int fm_get_components(fm_ctx *ctx, int stream, int t, int max_n, fm_component *out, int *n);
+
+/* Parity-test taps for frame t of the last call (host buffers, any may be NULL):
+ * gray, blur (masked) and dilated thresh are proc_height*proc_width uint8; bg is float64 and is
+ * the background AFTER the whole call (so compare it at t = n_frames-1).  gray/blur need
+ * FM_FLAG_KEEP_PLANES (the fused front end never materialises them otherwise). */
+int fm_debug_planes(fm_ctx *ctx, int stream, int t, uint8_t *gray, uint8_t *blur, uint8_t *thresh,
+                    double *bg);
+
+/* Parity-test tap for the mask raster: proc_height*proc_width uint8, 1 where blur is zeroed. */
+int fm_debug_mask(fm_ctx *ctx, int stream, uint8_t *mask);
+
+/* Parity-test entry for the contour stage alone: label a host uint8 plane (non-zero = set) of
+ * size h*w with findContours(RETR_EXTERNAL)+contourArea+boundingRect semantics. */
+int fm_debug_components(int device, const uint8_t *plane, int w, int h, int max_n,
+                        fm_component *out, int *n);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t fm_launch_count(void);
+
+/* Mean device time in ms of the kernels of group `which` (0 = front end, 1 = temporal, 2 =
+ * dilate+contours+decisions) over the calls since fm_timing_reset; needs fm_timing_enable(1),
+ * which brackets each group with CUDA events on the launching stream. */
+int fm_timing_enable(fm_ctx *ctx, int on);
+int fm_timing_reset(fm_ctx *ctx);
+int fm_timing_get(fm_ctx *ctx, int which, double *ms_total, int64_t *n_calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FM_GPU_H */

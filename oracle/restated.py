@@ -304,8 +304,8 @@ def fill_convex_poly(mask: np.ndarray, pts) -> None:
     if n < 3 or xmax < 0 or ymax < 0 or xmin >= w or ymin >= h:
         return
     ymax = min(ymax, h - 1)
-    edge = [{"idx": imin, "di": 1, "ye": ymin, "x": 0, "dx": 0},
-            {"idx": imin, "di": n - 1, "ye": ymin, "x": 0, "dx": 0}]
+    edge = [{"idx": imin, "di": 1, "ye": ymin, "x": -XY_ONE, "dx": 0},
+            {"idx": imin, "di": n - 1, "ye": ymin, "x": -XY_ONE, "dx": 0}]
     edges = n
     y = ymin
     left, right = 0, 1
@@ -317,8 +317,11 @@ def fill_convex_poly(mask: np.ndarray, pts) -> None:
                 idx = idx0 + di
                 if idx >= n:
                     idx -= n
-                ty = 0
-                while edges > 0:
+                while True:             # C: for (; edges-- > 0; )
+                    go = edges > 0
+                    edges -= 1
+                    if not go:
+                        break
                     ty = pts[idx][1]
                     if ty > y:
                         xs = pts[idx0][0]
@@ -333,7 +336,6 @@ def fill_convex_poly(mask: np.ndarray, pts) -> None:
                     idx += di
                     if idx >= n:
                         idx -= n
-                    edges -= 1
         if edges < 0:
             break
         if y >= 0:
