@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p frames/s of the motion-detection hot path on N B200s (+ HBM roofline).
+
+A step = one pass of the hot path (fm_process) over one batch of synthetic input: S streams x T
+frames of 1920x1080 BGR per GPU, taken from an HBM-resident ring of R frames per stream (ring >
+L2, so no step re-reads cached input).  Streams are independent, so ranks share nothing on the
+data path (weak scaling: S streams per GPU); the only collective is the max-over-ranks of the
+timed region.  `value` is whole-job frames/s with inputs resident in HBM; `e2e` is the same
+through the host-buffer entry point (fm_process_host: pinned host frames -> H2D -> kernels ->
+stats D2H, every step).  `--impl reference` times the reference's CPU path (the cv2 call chain
+of find_motion.py:852-904 re-typed in oracle/cv2_chain.py, one process per stream over all host
+cores, as run_pool does) on the same configuration.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+METRIC = "1080p frames/sec (whole box)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="full", choices=["full", "default"],
+                    help="full = --box-size 1920 (full-resolution stencil); default = reference default --box-size 100")
+    ap.add_argument("--blur-scale", type=int, default=None,
+                    help="reference --blur-scale; full mode default 384 (k=5, HBM-bound regime), 20 gives k=97")
+    ap.add_argument("--streams", type=int, default=8, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=16, help="T: frames per stream per step")
+    ap.add_argument("--ring", type=int, default=32, help="frames per stream resident in HBM")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary regimes (k=97, default mode)")
+    return ap.parse_args()
+
+
+def tuning(mode, blur_scale):
+    from find_motion_b200 import synth
+    kw = dict(fps=30, min_box_scale=50, threshold=12, avg=0.1, min_time=0.5, cache_time=1.0,
+              mask_areas=synth.CFG2_MASKS)
+    if mode == "full":
+        kw.update(box_size=W, blur_scale=blur_scale if blur_scale else 384)
+    else:
+        kw.update(box_size=100, blur_scale=blur_scale if blur_scale else 20)
+    return kw
+
+
+def bench_script(ring):
+    # one walker episode per ring pass, the rest quiet: a mix of motion and idle frames
+    return [("walker", ring // 4, ring // 4 + max(4, ring // 3)), ("hidden", 2, ring // 2)]
+
+
+def alg_bytes_per_frame(w, h, T, m=1.0 / 8):
+    """BGR in once + float64 background in/out once per T frames + m B/px mask out."""
+    return 3.0 * W * H + (16.0 / T) * w * h + m * w * h
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(kw, cores, target_s=2.5):
+    """Reference CPU path on a bounded sample: one stream per process over all host cores."""
+    from oracle import cv2_chain
+    probe = cv2_chain.time_cpu_path(W, H, kw, 1, 4, 1, clip_len=4)
+    per_frame = probe["seconds"] / 4
+    frames = max(4, min(400, int(target_s / per_frame)))
+    r = cv2_chain.time_cpu_path(W, H, kw, cores, frames, cores, clip_len=8)
+    return {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["processes"], "kind": "port",
+            "sample": f"{cores} synthetic 1080p streams x {frames} frames, one process per stream "
+                      f"({r['engine']}, cv2 threads/process = {r['cv_threads']}), decode/encode excluded",
+            "seconds": round(r["seconds"], 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kw = tuning(args.mode, args.blur_scale)
+    cores = os.cpu_count() or 1
+    from oracle import cv2_chain
+    probe = cv2_chain.time_cpu_path(W, H, kw, 1, 4, 1, clip_len=4)
+    frames = max(4, min(400, int(2.0 / (probe["seconds"] / 4))))
+    for _ in range(args.warmup):
+        cv2_chain.time_cpu_path(W, H, kw, cores, max(2, frames // 8), cores, clip_len=4)
+    tot_f, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        r = cv2_chain.time_cpu_path(W, H, kw, cores, frames, cores, clip_len=8)
+        tot_f += r["frames"]
+        tot_s += r["seconds"]
+    fps = tot_f / tot_s
+    info = probe_info(kw)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * tot_s / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+        "config": workload_config(args, kw, info),
+        "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} synthetic 1080p streams x {frames} frames per step, one process per "
+                                   f"stream ({r['engine']}, cv2 threads/process = 1), decode/encode excluded"},
+        "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def probe_info(kw):
+    from oracle import restated as R
+    return R.derive_params(W, H, kw["fps"], kw["box_size"], kw["min_box_scale"], kw["cache_time"], kw["min_time"],
+                           kw["blur_scale"])
+
+
+def workload_config(args, kw, info):
+    return {
+        "workload": f"BASELINE configs[1]/[2]: {args.streams} x 1080p30 synthetic streams per GPU "
+                    f"({args.streams * args.gpus} in the job; 64 at 8 GPUs = configs[2]), CFG2 polygon masks "
+                    f"(README square+triangle + translated pair), min-time/cache-time logic, "
+                    f"{'full-resolution' if args.mode == 'full' else 'reference-default'} mode",
+        "frame": f"{W}x{H} BGR u8", "proc": f"{info['w']}x{info['h']}", "gaussian": info["gaussian"],
+        "box_size": kw["box_size"], "blur_scale": kw["blur_scale"], "threshold": kw["threshold"], "avg": kw["avg"],
+        "min_time": kw["min_time"], "cache_time": kw["cache_time"], "fps": kw["fps"],
+        "streams_per_gpu": args.streams, "frames_per_step_per_stream": args.frames, "ring_frames": args.ring,
+        "l2_policy": f"inputs larger than L2: ring of {args.ring} frames/stream = "
+                     f"{args.streams * args.ring * W * H * 3 / 1e6:.0f} MB per GPU, each step reads the next T frames",
+        "parallelism": f"streams sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+
+
+def time_engine(eng, ring_dev, args, torch, dist, world):
+    """warm-up, then EXACTLY K timed steps bracketed by barrier + synchronize; returns ms (max over ranks)."""
+    R, T = args.ring, args.frames
+    nslots = R // T
+
+    def step(i):
+        a = (i % nslots) * T
+        eng.process(ring_dev[:, a:a + T], sync=False)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from find_motion_b200 import synth
+    from find_motion_b200.engine import MotionEngine, launch_count
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert args.ring % args.frames == 0 and args.ring >= args.frames
+
+    kw = tuning(args.mode, args.blur_scale)
+    S, T, R = args.streams, args.frames, args.ring
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(kw, os.cpu_count() or 1)
+        except Exception as e:   # never let the baseline kill the measurement
+            cpu = {"error": str(e)[:200]}
+
+    # synthetic streams: seed = 1000*cfg + global stream id, resident in HBM
+    ring_host = torch.empty((S, R, H, W, 3), dtype=torch.uint8).pin_memory()
+    for s in range(S):
+        clip = synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + s), script=bench_script(R))
+        ring_host[s] = torch.from_numpy(clip)
+    ring_dev = ring_host.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **kw)
+    info = dict(eng.info, w=eng.w, h=eng.h)
+    eng.timing(enable=True, reset=True)
+
+    sampler = ClockSampler(local)
+    # untimed priming pass so that the timing ring only sees the timed steps
+    for i in range(2):
+        eng.process(ring_dev[:, :T], sync=False)
+    torch.cuda.synchronize()
+    eng.reset()
+    eng.timing(reset=True)
+    l0 = launch_count()
+    sampler.start()
+    # NOTE: warm-up steps are launched inside time_engine; their group timings are subtracted below
+    ms = time_engine(eng, ring_dev, args, torch, dist, world)
+    clocks = sampler.stop()
+    launches_total = launch_count() - l0
+    groups = eng.timing()
+    calls = max(1, groups["front_end"][1])
+    launches = int(round(launches_total * args.steps / calls))          # timed steps only
+    frames_job = S * T * args.steps * world
+    fps = frames_job / (ms / 1e3)
+
+    # roofline of the dominant kernel group (CUDA events recorded on the launching stream)
+    per_call = {k: v[0] / max(1, v[1]) for k, v in groups.items()}
+    dom = max(per_call, key=per_call.get)
+    peak, peak_src = hbm_peak()
+    balg = alg_bytes_per_frame(info["proc_width"], info["proc_height"], T)
+    bytes_launch = balg * S * T
+    achieved = bytes_launch / (per_call[dom] / 1e3) / 1e9
+    step_ms = ms / args.steps
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": dom,
+                "kernel_ms_per_launch": round(per_call[dom], 4), "peak_source": peak_src,
+                "alg_bytes_per_frame": round(balg), "alg_formula": "3*W*H + (16/T)*w*h + m*w*h, m=1/8 (bit-packed mask)",
+                "groups_ms_per_step": {k: round(v, 4) for k, v in per_call.items()},
+                "whole_step_frac": round(bytes_launch / (step_ms / 1e3) / 1e9 / peak, 4)}
+
+    # end to end through the host-buffer entry point
+    eng.timing(enable=False)
+    eng.reset()
+    host_batch = [ring_host[:, a:a + T] for a in range(0, R, T)]
+    for i in range(2):
+        eng.process_host(host_batch[i % len(host_batch)])
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        eng.process_host(host_batch[i % len(host_batch)])
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = S * T * args.e2e_steps * world / e2e_s
+    e2e = {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": S * T * W * H * 3,
+           "d2h_bytes_per_step": S * T * 32, "steps": args.e2e_steps,
+           "api": "fm_process_host (MotionEngine.process_host), pinned host frames"}
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = secondary_regimes(args, ring_dev, torch, dist)
+
+    eng.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "config": workload_config(args, kw, info),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if extras:
+            line["other_regimes"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def secondary_regimes(args, ring_dev, torch, dist):
+    """Same streams in the other two regimes SURVEY.md 8(d) asks for (reported, not the headline)."""
+    from find_motion_b200.engine import MotionEngine
+    out = {}
+    S, T = args.streams, args.frames
+    for name, mode, bs in (("full_k97_alu_bound", "full", 20), ("default_box100", "default", 20)):
+        if mode == args.mode and (args.blur_scale or (384 if mode == "full" else 20)) == bs:
+            continue
+        kw = tuning(mode, bs)
+        try:
+            with MotionEngine(W, H, n_streams=S, max_frames=T, **kw) as eng:
+                a = argparse.Namespace(**vars(args))
+                a.steps, a.warmup = max(3, args.steps // 4), 3
+                ms = time_engine(eng, ring_dev, a, torch, dist, 1)
+                fps = S * T * a.steps / (ms / 1e3)
+                balg = alg_bytes_per_frame(eng.w, eng.h, T)
+                peak, _ = hbm_peak()
+                out[name] = {"value": round(fps, 1), "unit": "frames/s", "proc": f"{eng.w}x{eng.h}",
+                             "gaussian": eng.info["gaussian"], "steps": a.steps,
+                             "hbm_frac_whole_step": round(fps * balg / 1e9 / peak, 4)}
+        except Exception as e:
+            out[name] = {"error": str(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,7 @@
 #define FM_MAX_K 1024          // widest supported Gaussian (taps)
 #define FM_TILE_PX 512         // pixels per background tile: 32 lanes x 16 px
 #define FM_TILE_WORDS 16       // 32-bit threshold words per tile
+#define FM_TIMING_RING 1024
 
 struct StreamState {           // per stream, device resident (find_motion.py:362-371)
     int has_bg;                // ref_frame is not None
@@ -76,8 +77,9 @@ struct fm_ctx {
     fm_frame_stats *stats_pinned;
     cudaStream_t own_stream;
     // timing
-    bool timing;
-    cudaEvent_t ev[4];
+    bool timing;               // bracket the kernel groups with events (no sync inside fm_process)
+    cudaEvent_t *evs;          // [FM_TIMING_RING][4]
+    int ev_pending;
     double t_ms[3];
     int64_t t_calls;
 };

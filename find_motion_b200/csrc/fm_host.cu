@@ -131,8 +131,10 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     fm_ccl_free(&c->ccl);
     if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    for (int i = 0; i < 4; i++)
-        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->evs) {
+        for (int i = 0; i < 4 * FM_TIMING_RING; i++) cudaEventDestroy(c->evs[i]);
+        delete[] c->evs;
+    }
     delete c;
     return FM_OK;
 }
@@ -250,7 +252,6 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     int nb = (int)std::min<size_t>(F, std::max<size_t>(1, budget / per_frame));
     if ((rc = fm_ccl_alloc(&c->ccl, nb, c->h, cap))) return fail(rc);
     FM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; i++) FM_CUDA(cudaEventCreate(&c->ev[i]));
     *out = c;
     return FM_OK;
 }
@@ -294,6 +295,21 @@ extern "C" int fm_ctx_set_masks(fm_ctx *c, int stream, int n_polys, const int32_
 // --------------------------------------------------------------------------------------------
 // the hot path
 // --------------------------------------------------------------------------------------------
+static int timing_drain(fm_ctx *c) {
+    for (int i = 0; i < c->ev_pending; i++) {
+        cudaEvent_t *ev = c->evs + 4 * i;
+        FM_CUDA(cudaEventSynchronize(ev[3]));
+        for (int g = 0; g < 3; g++) {
+            float ms = 0;
+            FM_CUDA(cudaEventElapsedTime(&ms, ev[g], ev[g + 1]));
+            c->t_ms[g] += ms;
+        }
+        c->t_calls++;
+    }
+    c->ev_pending = 0;
+    return FM_OK;
+}
+
 extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
                           int n_frames, void *cuda_stream, fm_frame_stats *stats_dev) {
     if (!c || !frames) { fm_set_error("null argument"); return FM_EINVAL; }
@@ -305,27 +321,23 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
     const bool fused = false;
-    if (c->timing) FM_CUDA(cudaEventRecord(c->ev[0], st));
+    cudaEvent_t *ev = nullptr;
+    if (c->timing) {
+        if (c->ev_pending == FM_TIMING_RING && (rc = timing_drain(c))) return rc;
+        ev = c->evs + 4 * c->ev_pending++;
+        FM_CUDA(cudaEventRecord(ev[0], st));
+    }
     if (fused) {
         if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
-        if (c->timing) { FM_CUDA(cudaEventRecord(c->ev[1], st)); FM_CUDA(cudaEventRecord(c->ev[2], st)); }
+        if (ev) { FM_CUDA(cudaEventRecord(ev[1], st)); FM_CUDA(cudaEventRecord(ev[2], st)); }
     } else {
         if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
-        if (c->timing) FM_CUDA(cudaEventRecord(c->ev[1], st));
+        if (ev) FM_CUDA(cudaEventRecord(ev[1], st));
         if ((rc = fm_launch_temporal(c, n_frames, st))) return rc;
-        if (c->timing) FM_CUDA(cudaEventRecord(c->ev[2], st));
+        if (ev) FM_CUDA(cudaEventRecord(ev[2], st));
     }
     if ((rc = fm_launch_morph_ccl(c, n_frames, st, stats_dev))) return rc;
-    if (c->timing) {
-        FM_CUDA(cudaEventRecord(c->ev[3], st));
-        FM_CUDA(cudaEventSynchronize(c->ev[3]));
-        for (int i = 0; i < 3; i++) {
-            float ms = 0;
-            FM_CUDA(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
-            c->t_ms[i] += ms;
-        }
-        c->t_calls++;
-    }
+    if (ev) FM_CUDA(cudaEventRecord(ev[3], st));
     c->last_T = n_frames;
     c->planes_valid = true;
     return FM_OK;
@@ -465,17 +477,25 @@ extern "C" int fm_debug_components(int device, const uint8_t *plane, int w, int 
 
 extern "C" int fm_timing_enable(fm_ctx *c, int on) {
     if (!c) return FM_EINVAL;
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    if (on && !c->evs) {
+        c->evs = new cudaEvent_t[4 * FM_TIMING_RING];
+        for (int i = 0; i < 4 * FM_TIMING_RING; i++) FM_CUDA(cudaEventCreate(&c->evs[i]));
+    }
+    if (!on && c->ev_pending) { int rc = timing_drain(c); if (rc) return rc; }
     c->timing = on != 0;
     return FM_OK;
 }
 extern "C" int fm_timing_reset(fm_ctx *c) {
     if (!c) return FM_EINVAL;
+    if (c->ev_pending) { int rc = timing_drain(c); if (rc) return rc; }
     c->t_ms[0] = c->t_ms[1] = c->t_ms[2] = 0;
     c->t_calls = 0;
     return FM_OK;
 }
 extern "C" int fm_timing_get(fm_ctx *c, int which, double *ms_total, int64_t *n_calls) {
     if (!c || which < 0 || which > 2) return FM_EINVAL;
+    if (c->ev_pending) { int rc = timing_drain(c); if (rc) return rc; }
     if (ms_total) *ms_total = c->t_ms[which];
     if (n_calls) *n_calls = c->t_calls;
     return FM_OK;

@@ -98,44 +98,64 @@ class Cv2Stream:
 
 
 # ------------------------------------------------------------------------------------------
-# timing fan-out: one stream per pool task, like run_pool (find_motion.py:1054-1122)
+# timing fan-out: one stream per worker process, like run_pool (find_motion.py:1054-1122).
+# Workers are plain subprocesses (`python -m oracle.cv2_chain <json>`): forking a parent that has
+# already initialised cv2's thread pool or CUDA deadlocks, and spawn needs an importable main.
 # ------------------------------------------------------------------------------------------
 
-def _worker(args):
-    (W, H, n_frames, seed, clip_len, kw, cv_threads, use_cv2) = args
+def _worker(spec):
     from find_motion_b200 import synth
-    clip = synth.make_clip(W, H, clip_len, seed, fps=kw.get("fps", 30))
-    if use_cv2:
-        import cv2
-        cv2.setNumThreads(cv_threads)
-        st = Cv2Stream(W, H, **kw)
-        step = st.step
-    else:
-        from oracle import restated as R
-        so = R.StreamOracle(W, H, **kw)
-        step = so.process
-    t0 = time.perf_counter()
-    moved = 0
-    for i in range(n_frames):
-        moved += int(step(clip[i % clip_len])["movement"])
-    return time.perf_counter() - t0, moved
+    W, H, kw = spec["W"], spec["H"], spec["kw"]
+    if kw.get("mask_areas"):
+        kw["mask_areas"] = [tuple(tuple(p) for p in a) for a in kw["mask_areas"]]
+    out = []
+    for seed in spec["seeds"]:
+        clip = synth.make_clip(W, H, spec["clip_len"], seed, fps=kw.get("fps", 30))
+        if spec["use_cv2"]:
+            import cv2
+            cv2.setNumThreads(spec["cv_threads"])
+            step = Cv2Stream(W, H, **kw).step
+        else:
+            from oracle import restated as R
+            step = R.StreamOracle(W, H, **kw).process
+        t0 = time.perf_counter()
+        moved = 0
+        for i in range(spec["frames"]):
+            moved += int(step(clip[i % spec["clip_len"]])["movement"])
+        out.append({"seconds": time.perf_counter() - t0, "moved": moved})
+    return out
 
 
-def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8, seed0=2000, cv_threads=1):
-    """Run `n_streams` synthetic streams of `frames_per_stream` frames over a process pool.
-    Returns dict(fps, seconds, frames, processes, kind)."""
-    import multiprocessing as mp
+def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8, seed0=2000, cv_threads=1,
+                  timeout=600):
+    """Run `n_streams` synthetic streams of `frames_per_stream` frames over `processes` worker
+    processes (streams dealt round-robin).  Returns dict(fps, seconds, frames, processes, engine)."""
+    import json
+    import os
+    import subprocess
+    import sys
     use_cv2 = available()
-    tasks = [(W, H, frames_per_stream, seed0 + s, clip_len, kw, cv_threads, use_cv2) for s in range(n_streams)]
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(processes=processes) as pool:
-        res = pool.map(_worker, tasks, chunksize=1)
-    wall = time.perf_counter() - t0
-    busy = max(r[0] for r in res)
+    processes = max(1, min(processes, n_streams))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = []
+    for p in range(processes):
+        spec = {"W": W, "H": H, "kw": kw, "seeds": [seed0 + s for s in range(p, n_streams, processes)],
+                "clip_len": clip_len, "frames": frames_per_stream, "cv_threads": cv_threads, "use_cv2": use_cv2}
+        procs.append(subprocess.Popen([sys.executable, "-m", "oracle.cv2_chain", json.dumps(spec)], cwd=root,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    busy = 0.0
+    for pr in procs:
+        so, se = pr.communicate(timeout=timeout)
+        if pr.returncode != 0:
+            raise RuntimeError("cpu worker failed: " + se[-500:])
+        res = json.loads(so.strip().splitlines()[-1])
+        busy = max(busy, sum(r["seconds"] for r in res))     # a worker runs its streams back to back
     frames = n_streams * frames_per_stream
-    # clip synthesis happens inside the worker before its clock starts; use the slowest worker's
-    # loop time when every stream has its own process, else the wall clock
-    secs = busy if n_streams <= processes else wall
-    return {"fps": frames / secs, "seconds": secs, "frames": frames, "processes": min(processes, n_streams),
-            "engine": "cv2 call chain" if use_cv2 else "numpy oracle"}
+    return {"fps": frames / busy, "seconds": busy, "frames": frames, "processes": processes,
+            "engine": "cv2 call chain" if use_cv2 else "numpy oracle", "cv_threads": cv_threads}
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    print(json.dumps(_worker(json.loads(sys.argv[1]))))
