@@ -45,6 +45,7 @@ struct fm_ctx {
     int N;                     // w*h
     int ntiles;                // ceil(N / FM_TILE_PX)
     int resize_mode;           // 0 identity, 1 general tables, 2 integer ratio
+    bool fused;                // K1 fused stencil+background kernel drives the front end
     int fx, fy;                // integer ratios (mode 2)
     int maxc;
     // tables
@@ -120,6 +121,9 @@ int fm_launch_masks(fm_ctx *c, int stream, int n_polys, const int *offs, const i
 int fm_launch_bg_export(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st);
 int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st);
+bool fm_fused_supported(const fm_ctx *c);
+size_t fm_fused_bg_doubles(const fm_ctx *c);
+int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);
 void fm_ccl_free(CclScratch *s);
 int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out,

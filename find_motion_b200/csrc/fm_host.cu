@@ -208,7 +208,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
             if ((rc = upload_tab(&c->ytab, area_tab(c->H, c->h)))) return fail(rc);
         }
     }
-    inf.front_end = c->resize_mode == 0 ? 1 : 2;
+    c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);
+    inf.front_end = c->fused ? 0 : (c->resize_mode == 0 ? 1 : 2);
     if ((rc = upload(&c->coef, gauss_coeffs(c->k)))) return fail(rc);
 
     const size_t F = (size_t)c->S * c->Tmax;
@@ -225,7 +226,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->gray, F * c->N);
     ALLOC(c->hor, F * c->N * sizeof(uint16_t));
     ALLOC(c->blur, F * c->N + 64);
-    ALLOC(c->bg, (size_t)c->S * c->ntiles * FM_TILE_PX * sizeof(double));
+    const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX, c->fused ? fm_fused_bg_doubles(c) : (size_t)0);
+    ALLOC(c->bg, bg_doubles * sizeof(double));
     ALLOC(c->maskbits, (size_t)c->S * c->h * c->wpr * 4);
     ALLOC(c->maskflat, (size_t)c->S * flatw * 4);
     ALLOC(c->tflat, (F * flatw + FM_TILE_WORDS) * 4);
@@ -241,7 +243,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     FM_CUDA(cudaMemset(c->maskbits, 0, (size_t)c->S * c->h * c->wpr * 4));
     FM_CUDA(cudaMemset(c->maskflat, 0, (size_t)c->S * flatw * 4));
     FM_CUDA(cudaMemset(c->tflat, 0, (F * flatw + FM_TILE_WORDS) * 4));
-    FM_CUDA(cudaMemset(c->bg, 0, (size_t)c->S * c->ntiles * FM_TILE_PX * sizeof(double)));
+    FM_CUDA(cudaMemset(c->bg, 0, bg_doubles * sizeof(double)));
     FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
     FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
     // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
@@ -320,7 +322,7 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     FM_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
-    const bool fused = false;
+    const bool fused = c->fused;
     cudaEvent_t *ev = nullptr;
     if (c->timing) {
         if (c->ev_pending == FM_TIMING_RING && (rc = timing_drain(c))) return rc;
@@ -434,7 +436,7 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
     if (bg) {
         double *d = nullptr;
         FM_CUDA(cudaMalloc(&d, (size_t)c->N * sizeof(double)));
-        int rc = fm_launch_bg_export(c, stream, d, 0);
+        int rc = c->fused ? fm_launch_bg_export_fused(c, stream, d, 0) : fm_launch_bg_export(c, stream, d, 0);
         if (rc) return rc;
         FM_CUDA(cudaMemcpy(bg, d, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
         cudaFree(d);
@@ -501,7 +503,3 @@ extern "C" int fm_timing_get(fm_ctx *c, int which, double *ms_total, int64_t *n_
     return FM_OK;
 }
 
-int fm_launch_fused(fm_ctx *, const uint8_t *, size_t, size_t, int, cudaStream_t) {
-    fm_set_error("fused front end not built");
-    return FM_ERANGE;
-}

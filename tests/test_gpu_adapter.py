@@ -1,0 +1,89 @@
+"""GPU: the VideoMotion / run_vid drop-in writes exactly the frames the reference writes."""
+from collections import deque
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+class MemoryCapture:
+    """cv2.VideoCapture stand-in (get/read/isOpened/release)."""
+
+    def __init__(self, frames):
+        self.frames, self.i = frames, 0
+
+    def get(self, prop):
+        import cv2
+        return {cv2.CAP_PROP_FRAME_COUNT: float(len(self.frames)), cv2.CAP_PROP_FRAME_WIDTH: float(self.frames.shape[2]),
+                cv2.CAP_PROP_FRAME_HEIGHT: float(self.frames.shape[1])}.get(prop, 0.0)
+
+    def isOpened(self):
+        return True
+
+    def read(self):
+        if self.i >= len(self.frames):
+            return False, None
+        self.i += 1
+        return True, self.frames[self.i - 1]
+
+    def release(self):
+        pass
+
+
+def expected_written(trace, cache_frames):
+    """Replay decide_output (find_motion.py:549-589) on frame indices from the golden decisions."""
+    out, cache = [], deque(maxlen=cache_frames)
+    for t, e in enumerate(trace):
+        if e["wrote"]:
+            if e["n_flush"]:
+                out += list(cache)
+                cache.clear()
+            out.append(t)
+        else:
+            cache.append(t)
+    return out
+
+
+@pytest.mark.parametrize("name,chunk", [("cfg1_640x480_default", 16), ("full_256x192_k5", 5),
+                                        ("full_320x240_k17_masks", 32)])
+def test_adapter_writes_reference_frames(name, chunk):
+    pytest.importorskip("cv2")
+    from find_motion_b200.video_motion import VideoMotion
+    fx = helpers.load_golden(name)
+    clip = helpers.golden_clip(fx)
+    # tag every frame so that written frames can be identified
+    written = []
+
+    class Recorder(VideoMotion):
+        def _make_outfile(self):
+            self.outfiles += 1
+
+            class W:
+                def write(_, frame):
+                    written.append(frame)
+
+                def release(_):
+                    pass
+            self.outfile = W()
+
+    vm = Recorder(MemoryCapture(clip), chunk=chunk, **fx["kwargs"])
+    assert vm.loaded
+    assert vm.cache_frames == fx["params"]["cache_frames"] and vm.max_area == fx["params"]["max_area"]
+    wrote, err, seen = vm.find_motion()
+    assert err == "" and seen == ()
+    assert wrote == fx["result"][0]
+    want = expected_written(fx["trace"], fx["params"]["cache_frames"])
+    assert len(written) == len(want) == fx["writes"]
+    for frame, t in zip(written, want):
+        assert frame is clip[t] or (frame == clip[t]).all()
+
+
+def test_run_vid_reports_errors_like_the_reference():
+    from find_motion_b200.video_motion import run_vid
+    res = run_vid(None)
+    assert res[0] is None and "Filename required" in res[2]
+    res = run_vid("/nonexistent/file.avi", box_size=100)
+    assert res[0] is None and res[2] != ""
