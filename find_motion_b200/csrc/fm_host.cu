@@ -423,6 +423,10 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
     FM_CUDA(cudaSetDevice(c->cfg.device));
     FM_CUDA(cudaDeviceSynchronize());
     size_t f = (size_t)stream * c->last_T + t;
+    if ((gray || blur) && c->fused && !(c->cfg.flags & FM_FLAG_KEEP_PLANES)) {
+        fm_set_error("gray/blur planes are not materialised by the fused front end without FM_FLAG_KEEP_PLANES");
+        return FM_EINVAL;
+    }
     if (gray) FM_CUDA(cudaMemcpy(gray, c->gray + f * c->N, c->N, cudaMemcpyDeviceToHost));
     if (blur) FM_CUDA(cudaMemcpy(blur, c->blur + f * c->N, c->N, cudaMemcpyDeviceToHost));
     if (thresh) {

@@ -134,7 +134,7 @@ def test_streams_are_independent():
     clips = np.stack([synth.make_clip(W, H, n, seed=50 + s, fps=6) for s in range(3)])
     oracles = [R.StreamOracle(W, H, **kw) for _ in range(3)]
     dev = torch.from_numpy(clips).cuda()
-    with MotionEngine(W, H, n_streams=3, max_frames=T, **kw) as eng:
+    with MotionEngine(W, H, n_streams=3, max_frames=T, keep_planes=True, **kw) as eng:
         for t0 in range(0, n, T):
             stats = eng.process(dev[:, t0:t0 + T])
             for s in range(3):
