@@ -13,6 +13,8 @@
 // Packed arithmetic: for k in {1,3,5} the taps are g*[b0,b1,b2,b1,b0] with g >= 16, so the
 // horizontal sums (<= 255*256/g) and the vertical sums (<= 255*(256/g)^2 <= 65280) fit 16 bits
 // and two pixels share one 32-bit IMAD; (ver + 32768) >> 16 == (v' + round) >> shift exactly.
+#include <cuda.h>
+
 #include "fm_common.cuh"
 
 #define FT_W 128
@@ -20,10 +22,37 @@
 #define FG_WORDS 34        // gray words per shared row: cols x0-4 .. x0+131
 #define FG_ROWS 68         // rows y0-2 .. y0+65
 #define FUSED_THREADS 256
+#define RAW_PITCH 416      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+399 (TMA box of 104 u32)
+#define RAW_STAGE (RAW_PITCH * FG_ROWS)
+
+// ---- TMA / mbarrier primitives (sm_100a PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 struct FusedParams {
-    const uint8_t *frames;
-    size_t sstride, fstride;
     int T, w, h, wpr;
     int tilesX, tilesY;
     double *bg;                 // [S][tiles][8 warps][8 rows][2 pairs][32 lanes] double2
@@ -38,19 +67,18 @@ struct FusedParams {
 };
 
 __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
-    // 4 BGR pixels in 3 words -> 4 gray bytes.  Y = (3735 B + 19235 G + 9798 R + 16384) >> 15 with the
-    // coefficients split in bytes: c = 256*hi + lo, two dp4a per pixel.
-    const uint32_t LO_A = 151u | (35u << 8) | (70u << 16);        // bytes [B,G,R,x]
-    const uint32_t HI_A = 14u | (75u << 8) | (38u << 16);
-    const uint32_t LO_D = (151u << 8) | (35u << 16) | (70u << 24);   // bytes [x,B,G,R]
-    const uint32_t HI_D = (14u << 8) | (75u << 16) | (38u << 24);
-    uint32_t p1 = __funnelshift_r(w0, w1, 24);                       // [B1,G1,R1,B2]
-    uint32_t p2 = __funnelshift_r(w1, w2, 16);                       // [B2,G2,R2,B3]
-    uint32_t y0 = (__dp4a(w0, HI_A, 0u) * 256u + __dp4a(w0, LO_A, 16384u)) >> 15;
-    uint32_t y1 = (__dp4a(p1, HI_A, 0u) * 256u + __dp4a(p1, LO_A, 16384u)) >> 15;
-    uint32_t y2 = (__dp4a(p2, HI_A, 0u) * 256u + __dp4a(p2, LO_A, 16384u)) >> 15;
-    uint32_t y3 = (__dp4a(w2, HI_D, 0u) * 256u + __dp4a(w2, LO_D, 16384u)) >> 15;
-    return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    // 4 BGR pixels in 3 words -> 4 gray bytes.  Y = (3735 B + 19235 G + 9798 R + 16384) >> 15 computed as
+    // (7470 B + 38470 G + 19596 R + 32768) >> 16 with two 16-bit x 8-bit dot products per pixel (IDP.2A);
+    // the result is byte 2 of the accumulator.
+    const uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u;              // bytes [B,G,R,x]
+    const uint32_t C_xB = 7470u << 16, C_GR = 38470u | (19596u << 16);       // bytes [x,B,G,R]
+    uint32_t p1 = __funnelshift_r(w0, w1, 24);                               // [B1,G1,R1,B2]
+    uint32_t p2 = __funnelshift_r(w1, w2, 16);                               // [B2,G2,R2,B3]
+    uint32_t t0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, 32768u));
+    uint32_t t1 = __dp2a_hi(C_R, p1, __dp2a_lo(C_BG, p1, 32768u));
+    uint32_t t2 = __dp2a_hi(C_R, p2, __dp2a_lo(C_BG, p2, 32768u));
+    uint32_t t3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_xB, w2, 32768u));
+    return __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);
 }
 
 __device__ __forceinline__ double u8_to_f64(uint32_t v) {
@@ -77,9 +105,67 @@ __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
     return x;
 }
 
+// One thread: 12 gray rows in -> 8 output rows x 4 pixels: blur, mask, threshold bits, background update.
+// INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels.
+template <bool KEEP, bool SAFE, bool INIT, bool MASKED>
+__device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)[32], uint32_t M, const FusedParams &p,
+                                               uint8_t *blur_out, int rows_valid) {
+    const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
+    const int qoff = 0x4B400000 - p.threshold;
+    const unsigned thr2 = 2u * (unsigned)p.threshold;
+    uint32_t win[5][2];
+    uint32_t bits = 0;
+#pragma unroll
+    for (int rr = 0; rr < 12; rr++) {
+        uint32_t W0 = sgw[rr * FG_WORDS], W1 = sgw[rr * FG_WORDS + 1], W2 = sgw[rr * FG_WORDS + 2];
+        uint32_t Ea = __byte_perm(W0, 0, 0x4342), Eb = __byte_perm(W1, 0, 0x4140);
+        uint32_t Ec = __byte_perm(W1, 0, 0x4342), Ed = __byte_perm(W2, 0, 0x4140);
+        uint32_t Oa = __funnelshift_r(Ea, Eb, 16), Ob = __funnelshift_r(Eb, Ec, 16), Oc = __funnelshift_r(Ec, Ed, 16);
+        uint32_t h0 = b0 * (Ea + Ec) + b1 * (Oa + Ob) + b2 * Eb;
+        uint32_t h1 = b0 * (Eb + Ed) + b1 * (Ob + Oc) + b2 * Ec;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { win[i][0] = win[i + 1][0]; win[i][1] = win[i + 1][1]; }
+        win[4][0] = h0;
+        win[4][1] = h1;
+        if (rr >= 4) {
+            const int r = rr - 4;          // output row of this thread
+            uint32_t v[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
+                v[j] = (a >> p.shift) & 0x00FF00FFu;
+            }
+            if (KEEP) {
+                if (r < rows_valid) {
+                    uint32_t o = (v[0] & 0xFF) | ((v[0] >> 16) << 8) | ((v[1] & 0xFF) << 16) | ((v[1] >> 16) << 24);
+                    uint32_t mk = (M >> (4 * r)) & 0xFu;
+                    uint32_t keep = ((mk & 1) ? 0u : 0xFFu) | ((mk & 2) ? 0u : 0xFF00u) | ((mk & 4) ? 0u : 0xFF0000u) |
+                                    ((mk & 8) ? 0u : 0xFF000000u);
+                    *reinterpret_cast<uint32_t *>(blur_out + (size_t)r * p.w) = o & keep;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int idx = 4 * r + c;
+                uint32_t sv = (c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu);
+                if (MASKED && (M & (1u << idx))) sv = 0;          // mask_off_areas paints BLACK into blur
+                const double sd = u8_to_f64(sv);
+                if (INIT) bg[idx] = sd;                           // ref_frame = blur.astype(float)
+                int q = bg8_magic<SAFE>(bg[idx]);
+                if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;   // |bg8 - blur| > threshold
+                bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
+            }
+        }
+    }
+    return bits;
+}
+
 template <bool KEEP, bool SAFE>
-__global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(FusedParams p) {
-    __shared__ uint32_t sg[FG_ROWS * FG_WORDS];
+__global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constant__ CUtensorMap tmap, FusedParams p) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    unsigned char *raw = fsm;                                                  // [2][RAW_STAGE] staged BGR rows (TMA)
+    uint32_t *sg = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);        // [FG_ROWS][FG_WORDS] gray
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + 2 * RAW_STAGE + FG_ROWS * FG_WORDS * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.y;
     const int tile = blockIdx.x;
@@ -114,22 +200,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(FusedParams p) {
             }
         }
     }
-    const uint8_t *src = p.frames + (size_t)s * p.sstride;
+    // TMA pipeline: frame t+1 lands in the other stage while frame t is being processed
+    const int cx = (x0 * 3) / 4 - 4, cy = y0 - 2;        // box origin in (u32 column, row); OOB is zero-filled
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], RAW_STAGE);
+        tma_load_4d(raw, &tmap, &bars[0], cx, cy, 0, s);
+    }
     uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords;
-    const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
 
     for (int t = 0; t < p.T; t++) {
-        __syncthreads();            // previous frame's readers are done with sg
-        // ---- BGR -> gray into shared memory (tile + halo), 4 pixels per unit ----
-        for (int u = tid; u < FG_ROWS * FG_WORDS; u += FUSED_THREADS) {
-            int ry = u / FG_WORDS, ux = u - ry * FG_WORDS;
-            int gy = y0 - 2 + ry, gx = x0 - 4 + 4 * ux;
-            uint32_t g = 0;
-            if ((unsigned)gy < (unsigned)h && (unsigned)gx < (unsigned)w) {
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(src + ((size_t)gy * w + gx) * 3);
-                g = gray4(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+        __syncthreads();            // everyone is done with gray(t-1) and with raw stage (t+1)&1
+        if (tid == 0 && t + 1 < p.T) {
+            mbar_expect_tx(&bars[(t + 1) & 1], RAW_STAGE);
+            tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, t + 1, s);
+        }
+        mbar_wait(&bars[t & 1], (t >> 1) & 1);
+        // ---- staged BGR -> gray bytes in shared memory (tile + halo), 4 pixels per unit ----
+        {
+            const unsigned char *rs = raw + (t & 1) * RAW_STAGE + 4;
+#pragma unroll 3
+            for (int u = tid; u < FG_ROWS * FG_WORDS; u += FUSED_THREADS) {
+                int ry = u / FG_WORDS, ux = u - ry * FG_WORDS;
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + ry * RAW_PITCH + ux * 12);
+                sg[u] = gray4(q[0], q[1], q[2]);
             }
-            sg[u] = g;
         }
         __syncthreads();
         if (border) {               // BORDER_REFLECT_101 for the 2-pixel ring outside the image
@@ -161,51 +262,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(FusedParams p) {
         }
         // ---- separable blur on packed pairs, sliding 5-row window, then the temporal update ----
         const uint32_t *sgw = sg + (8 * warp) * FG_WORDS + lane;
-        uint32_t win[5][2];
-        uint32_t bits = 0;
-#pragma unroll
-        for (int rr = 0; rr < 12; rr++) {
-            uint32_t W0 = sgw[rr * FG_WORDS], W1 = sgw[rr * FG_WORDS + 1], W2 = sgw[rr * FG_WORDS + 2];
-            uint32_t Ea = __byte_perm(W0, 0, 0x4342), Eb = __byte_perm(W1, 0, 0x4140);
-            uint32_t Ec = __byte_perm(W1, 0, 0x4342), Ed = __byte_perm(W2, 0, 0x4140);
-            uint32_t Oa = __funnelshift_r(Ea, Eb, 16), Ob = __funnelshift_r(Eb, Ec, 16), Oc = __funnelshift_r(Ec, Ed, 16);
-            uint32_t h0 = b0 * (Ea + Ec) + b1 * (Oa + Ob) + b2 * Eb;
-            uint32_t h1 = b0 * (Eb + Ed) + b1 * (Ob + Oc) + b2 * Ec;
-#pragma unroll
-            for (int i = 0; i < 4; i++) { win[i][0] = win[i + 1][0]; win[i][1] = win[i + 1][1]; }
-            win[4][0] = h0;
-            win[4][1] = h1;
-            if (rr >= 4) {
-                const int r = rr - 4;          // output row of this thread
-                uint32_t v[2];
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
-                    v[j] = (a >> p.shift) & 0x00FF00FFu;
-                }
-                if (KEEP) {
-                    int y = py + r;
-                    if (y < h && px < w) {
-                        uint32_t o = (v[0] & 0xFF) | ((v[0] >> 16) << 8) | ((v[1] & 0xFF) << 16) | ((v[1] >> 16) << 24);
-                        uint32_t mk = (M >> (4 * r)) & 0xFu;
-                        uint32_t keep = ((mk & 1) ? 0u : 0xFFu) | ((mk & 2) ? 0u : 0xFF00u) | ((mk & 4) ? 0u : 0xFF0000u) |
-                                        ((mk & 8) ? 0u : 0xFF000000u);
-                        *reinterpret_cast<uint32_t *>(p.blur_out + (((size_t)s * p.T + t) * h + y) * w + px) = o & keep;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int idx = 4 * r + c;
-                    uint32_t sv = (c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu);
-                    if (M & (1u << idx)) sv = 0;                    // mask_off_areas paints BLACK into blur
-                    if (t == 0 && !has_bg) bg[idx] = u8_to_f64(sv); // ref_frame = blur.astype(float)
-                    int q = bg8_magic<SAFE>(bg[idx]);
-                    int d = q - (0x4B400000 + (int)sv);
-                    if ((unsigned)(d + p.threshold) > (unsigned)(2 * p.threshold)) bits |= 1u << idx;
-                    bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(u8_to_f64(sv), p.alpha));
-                }
-            }
-        }
+        uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.T + t) * h + py) * w + px : nullptr;
+        const bool okx = px < w;
+        uint32_t bits;
+        if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        else if (M) bits = fused_rows<KEEP, SAFE, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        else bits = fused_rows<KEEP, SAFE, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
         // ---- 8 lanes x 8 rows of nibbles -> one 32-pixel word per lane, coalesced store ----
         uint32_t word = nibble_transpose8(bits, lane);
         {
@@ -214,7 +276,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(FusedParams p) {
             if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
         }
         tw += p.flatwords;
-        src += p.fstride;
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
@@ -235,7 +296,7 @@ __global__ void k_bg_export_fused(const double *__restrict__ bg, double *__restr
 
 bool fm_fused_supported(const fm_ctx *c) {
     return c->resize_mode == 0 && c->k <= 5 && (c->w % 32) == 0 && c->w >= 4 && c->h >= 4 &&
-           ((size_t)c->W * c->H * 3) % 4 == 0;
+           ((size_t)c->W * c->H * 3) % 16 == 0;
 }
 
 size_t fm_fused_bg_doubles(const fm_ctx *c) {
@@ -243,13 +304,42 @@ size_t fm_fused_bg_doubles(const fm_ctx *c) {
     return (size_t)c->S * tilesX * tilesY * FT_W * FT_H;
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)sym;
+    }
+    return fn;
+}
+
+#define FUSED_SMEM (2 * RAW_STAGE + FG_ROWS * FG_WORDS * 4 + 16)
+
 int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
-    if ((((uintptr_t)frames) & 3) || (sstride & 3) || (fstride & 3)) {
-        fm_set_error("fused front end needs 4-byte aligned frames and strides");
+    if ((((uintptr_t)frames) & 15) || (sstride & 15) || (fstride & 15)) {
+        fm_set_error("fused front end needs 16-byte aligned frames and strides (TMA)");
         return FM_EINVAL;
     }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { fm_set_error("cuTensorMapEncodeTiled not available"); return FM_ECUDA; }
+    // the call's frames as a 4-D u32 tensor: (W*3/4 words, H rows, T frames, S streams)
+    CUtensorMap tmap;
+    cuuint64_t dims[4] = {(cuuint64_t)c->W * 3 / 4, (cuuint64_t)c->H, (cuuint64_t)T, (cuuint64_t)c->S};
+    cuuint64_t strides[3] = {(cuuint64_t)c->W * 3, (cuuint64_t)fstride, (cuuint64_t)(c->S > 1 ? sstride : fstride * T)};
+    cuuint32_t box[4] = {RAW_PITCH / 4, FG_ROWS, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void *)frames, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fm_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FM_ECUDA; }
     FusedParams p;
-    p.frames = frames; p.sstride = sstride; p.fstride = fstride;
     p.T = T; p.w = c->w; p.h = c->h; p.wpr = c->wpr;
     p.tilesX = (c->w + FT_W - 1) / FT_W; p.tilesY = (c->h + FT_H - 1) / FT_H;
     p.bg = c->bg; p.maskbits = c->maskbits; p.tbits = c->tflat;
@@ -269,12 +359,20 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
     const bool keep = (c->cfg.flags & FM_FLAG_KEEP_PLANES) != 0;
     const bool safe = p.alpha >= 0.0 && p.alpha <= 1.0 && p.threshold >= 0;
     dim3 grid(p.tilesX * p.tilesY, c->S);
+    static bool configured = false;
+    if (!configured) {
+        FM_CUDA(cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(k_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        configured = true;
+    }
     if (keep) {
-        if (safe) k_fused<true, true><<<grid, FUSED_THREADS, 0, st>>>(p);
-        else k_fused<true, false><<<grid, FUSED_THREADS, 0, st>>>(p);
+        if (safe) k_fused<true, true><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);
+        else k_fused<true, false><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);
     } else {
-        if (safe) k_fused<false, true><<<grid, FUSED_THREADS, 0, st>>>(p);
-        else k_fused<false, false><<<grid, FUSED_THREADS, 0, st>>>(p);
+        if (safe) k_fused<false, true><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);
+        else k_fused<false, false><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);
     }
     FM_LAUNCH_CHECK();
     return FM_OK;
