@@ -233,7 +233,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->tflat, (F * flatw + FM_TILE_WORDS) * 4);
     ALLOC(c->dil, F * c->h * c->wpr * 4);
     ALLOC(c->fill, F * c->h * c->wpr * 4);
-    ALLOC(c->any, F * sizeof(int));
+    ALLOC(c->any, F * 2 * sizeof(int));      // per frame: row range of the dilated mask
     ALLOC(c->ncomp, F * sizeof(int));
     ALLOC(c->ncounted, F * sizeof(int));
     ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
@@ -247,10 +247,10 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
     FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
     // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
-    // most w/4 + 2 runs of either polarity; sub-batch sized to ~1.5 GB
+    // most w/4 + 2 runs of either polarity; sub-batch sized to <= 8 GB (only the slots of existing runs are ever touched)
     int cap = c->w / 4 + 3;
     size_t per_frame = (size_t)c->h * cap * 28 + (size_t)c->h * 4 + 4;
-    size_t budget = (size_t)1536 << 20;
+    size_t budget = (size_t)8 << 30;
     int nb = (int)std::min<size_t>(F, std::max<size_t>(1, budget / per_frame));
     if ((rc = fm_ccl_alloc(&c->ccl, nb, c->h, cap))) return fail(rc);
     FM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));

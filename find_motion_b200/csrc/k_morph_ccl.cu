@@ -38,13 +38,17 @@ __device__ __forceinline__ uint32_t flat_row_word(const uint32_t *flat, int y, i
     return v;
 }
 
+// rowrange[2f] = max y with a set pixel (-1: none), rowrange[2f+1] = max (h-1-y)  (memset 0xFF before)
+template <bool ALIGNED>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t *__restrict__ tflat,
-                                                                 uint32_t *__restrict__ dil, int *__restrict__ any,
-                                                                 int F, int w, int h, int wpr, int flatwords) {
+                                                                 uint32_t *__restrict__ dil, int *__restrict__ rowrange,
+                                                                 const int *__restrict__ rawany, int F, int w, int h,
+                                                                 int wpr, int flatwords) {
     int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (warp >= F * h) return;
     int f = warp / h, y = warp - f * h;
+    if (rawany && !rawany[f]) return;          // nothing above threshold in this frame: plane is all zero
     const uint32_t *flat = tflat + (size_t)f * flatwords;
     uint32_t *out = dil + ((size_t)f * h + y) * wpr;
     uint32_t anyw = 0;
@@ -52,9 +56,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t 
         uint32_t vm = 0, vc = 0, vp = 0;    // vertical OR of words j-1, j, j+1
 #pragma unroll
         for (int dy = -2; dy <= 2; dy++) {
-            vm |= flat_row_word(flat, y + dy, j - 1, w, h, wpr);
-            vc |= flat_row_word(flat, y + dy, j, w, h, wpr);
-            vp |= flat_row_word(flat, y + dy, j + 1, w, h, wpr);
+            int yy = y + dy;
+            if (ALIGNED) {                  // w % 32 == 0: flat order == row-padded order
+                if ((unsigned)yy < (unsigned)h) {
+                    const uint32_t *r = flat + (size_t)yy * wpr;
+                    vc |= __ldg(r + j);
+                    if (j > 0) vm |= __ldg(r + j - 1);
+                    if (j + 1 < wpr) vp |= __ldg(r + j + 1);
+                }
+            } else {
+                vm |= flat_row_word(flat, yy, j - 1, w, h, wpr);
+                vc |= flat_row_word(flat, yy, j, w, h, wpr);
+                vp |= flat_row_word(flat, yy, j + 1, w, h, wpr);
+            }
         }
         uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) |
                      (vp << 30);
@@ -63,27 +77,36 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t 
         out[j] = d;
         anyw |= d;
     }
-    if (__any_sync(0xffffffffu, anyw != 0) && lane == 0) atomicOr(any + f, 1);
+    if (__any_sync(0xffffffffu, anyw != 0) && lane == 0) {
+        atomicMax(rowrange + 2 * f, y);
+        atomicMax(rowrange + 2 * f + 1, h - 1 - y);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // run extraction
 // ---------------------------------------------------------------------------------------------
 struct CclArgs {
-    const uint32_t *plane;     // [F][h][wpr] bit plane of this pass
-    const int *any;            // [F] skip frames without set pixels (may be NULL)
+    const uint32_t *plane;     // [F][h][wpr] dilated bit plane
+    uint32_t *fill;            // [F][h][wpr] dilated plane with holes filled (written by the kernel)
+    const int *rowrange;       // [F][2] from k_dilate (NULL: label every row of every frame)
     int f0, nf;                // frames [f0, f0+nf) of the call are in this sub-batch
     int w, h, wpr, cap;
     size_t slots;
     uint16_t *xs, *xe;
     int *rowcnt, *parent, *area2, *bbox;
     int *errflag;
+    int *ncomp, *ncounted;     // [F]
+    fm_component *comps;       // [F][maxc]
+    int maxc, min_area, max_area;
 };
 
+// INVERT: runs of zeros (background pass).  Planes written earlier in the same kernel are read
+// with ld.global.cg (L2), never through the non-coherent path.
 template <bool INVERT>
 __device__ __forceinline__ uint32_t plane_word(const uint32_t *row, int j, int w, int wpr) {
     if ((unsigned)j >= (unsigned)wpr) return 0u;
-    uint32_t v = __ldg(row + j);
+    uint32_t v = __ldcg(row + j);
     if (INVERT) {
         v = ~v;
         int rem = w - 32 * j;
@@ -93,17 +116,10 @@ __device__ __forceinline__ uint32_t plane_word(const uint32_t *row, int j, int w
 }
 
 template <bool INVERT>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_runs(CclArgs a) {
-    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (warp >= a.nf * a.h) return;
-    int lf = warp / a.h, y = warp - lf * a.h;
-    int f = a.f0 + lf;
-    if (a.any && !a.any[f]) return;
-    const uint32_t *row = a.plane + ((size_t)f * a.h + y) * a.wpr;
+__device__ __forceinline__ void runs_row(const CclArgs &a, const uint32_t *plane, int lf, int f, int y, int lane) {
+    const uint32_t *row = plane + ((size_t)f * a.h + y) * a.wpr;
     size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
     int *parent = a.parent + (size_t)lf * (a.slots + 1);
-    if (y == 0 && lane == 0) parent[0] = 0;      // the outside node
     int nstart = 0, nend = 0;
     for (int j0 = 0; j0 < a.wpr; j0 += 32) {
         int j = j0 + lane;
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_runs(CclArgs a) {
         uint32_t Bn = plane_word<INVERT>(row, j + 1, a.w, a.wpr);
         uint32_t S = B & ~((B << 1) | (Bp >> 31));
         uint32_t E = B & ~((B >> 1) | (Bn << 31));
+        if (!__any_sync(0xffffffffu, (S | E) != 0)) continue;      // no run starts or ends in these 1024 pixels
         int cs = __popc(S), ce = __popc(E);
         int ps = cs, pe = ce;     // inclusive warp scans
 #pragma unroll
@@ -160,10 +177,23 @@ __device__ __forceinline__ int uf_find(const int *parent, int x) {
     return x;
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent.  Links only ever
+// decrease (atomicMin), so concurrent unions stay correct.
+__device__ __forceinline__ int uf_find_compress(int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        int gp = __ldcg(parent + p);
+        if (gp != p) atomicMin(parent + x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
 __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_compress(parent, a);
+        b = uf_find_compress(parent, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
         int old = atomicMin(parent + a, b);
@@ -174,19 +204,14 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 
 // CONN8: runs of adjacent rows touch if their x ranges overlap after growing by one pixel.
 // OUTSIDE: runs that touch the image border are linked to the outside node (background pass).
+// ylo: first labelled row (runs of row ylo have no labelled predecessor row).
 template <bool CONN8, bool OUTSIDE>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_union(CclArgs a) {
-    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (warp >= a.nf * a.h) return;
-    int lf = warp / a.h, y = warp - lf * a.h;
-    int f = a.f0 + lf;
-    if (a.any && !a.any[f]) return;
+__device__ __forceinline__ void union_row(const CclArgs &a, int lf, int y, int ylo, int lane) {
     int n = a.rowcnt[(size_t)lf * a.h + y];
     if (n == 0) return;
     size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
     int *parent = a.parent + (size_t)lf * (a.slots + 1);
-    int np = y > 0 ? a.rowcnt[(size_t)lf * a.h + y - 1] : 0;
+    int np = y > ylo ? a.rowcnt[(size_t)lf * a.h + y - 1] : 0;
     const uint16_t *pxs = a.xs + base - a.cap, *pxe = a.xe + base - a.cap;
     const int d = CONN8 ? 1 : 0;
     for (int i = lane; i < n; i += 32) {
@@ -206,16 +231,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_union(CclArgs a) {
 }
 
 // background pass epilogue: F = plane | (background runs not connected to the outside)
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_fill_holes(CclArgs a, uint32_t *__restrict__ fill) {
-    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (warp >= a.nf * a.h) return;
-    int lf = warp / a.h, y = warp - lf * a.h;
-    int f = a.f0 + lf;
-    if (a.any && !a.any[f]) return;
+__device__ __forceinline__ void fill_row(const CclArgs &a, int lf, int f, int y, int lane) {
     const uint32_t *row = a.plane + ((size_t)f * a.h + y) * a.wpr;
-    uint32_t *out = fill + ((size_t)f * a.h + y) * a.wpr;
-    for (int j = lane; j < a.wpr; j += 32) out[j] = row[j];
+    uint32_t *out = a.fill + ((size_t)f * a.h + y) * a.wpr;
+    for (int j = lane; j < a.wpr; j += 32) out[j] = __ldcg(row + j);
     __syncwarp();
     int n = a.rowcnt[(size_t)lf * a.h + y];
     size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
@@ -232,18 +251,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_fill_holes(CclArgs a, 
 }
 
 // per run: bit-quad area contribution (windows whose lower row is y) and bounding box -> root
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_run_stats(CclArgs a) {
-    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (warp >= a.nf * a.h) return;
-    int lf = warp / a.h, y = warp - lf * a.h;
-    int f = a.f0 + lf;
-    if (a.any && !a.any[f]) return;
+__device__ __forceinline__ void stats_row(const CclArgs &a, int lf, int f, int y, int lane) {
     int n = a.rowcnt[(size_t)lf * a.h + y];
     if (n == 0) return;
     size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
     const int *parent = a.parent + (size_t)lf * (a.slots + 1);
-    const uint32_t *up = a.plane + ((size_t)f * a.h + y - 1) * a.wpr;   // row y-1 (unused for y == 0)
+    const uint32_t *up = a.fill + ((size_t)f * a.h + (y > 0 ? y - 1 : 0)) * a.wpr;   // row y-1 (unused for y == 0)
     for (int i = lane; i < n; i += 32) {
         int xs = a.xs[base + i], xe = a.xe[base + i];
         int root = uf_find(parent, 1 + y * a.cap + i) - 1;
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_run_stats(CclArgs a) {
             if (xe > xs) {
                 int x0 = xs, x1 = xe - 1;
                 for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
-                    uint32_t U = ld_word(up, j, a.wpr), Un = ld_word(up, j + 1, a.wpr);
+                    uint32_t U = plane_word<false>(up, j, a.w, a.wpr), Un = plane_word<false>(up, j + 1, a.w, a.wpr);
                     uint32_t Us = (U >> 1) | (Un << 31);            // bit i = pixel x+1
                     int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
                     uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_run_stats(CclArgs a) {
             // windows x = xs-1 (lower 0,1) and x = xe (lower 1,0): need both upper pixels
             auto ubit = [&](int x) -> uint32_t {
                 if (x < 0 || x >= a.w) return 0u;
-                return (__ldg(up + (x >> 5)) >> (x & 31)) & 1u;
+                return (__ldcg(up + (x >> 5)) >> (x & 31)) & 1u;
             };
             q += (int)(ubit(xs - 1) & ubit(xs)) + (int)(ubit(xe) & ubit(xe + 1));
         }
@@ -277,35 +290,59 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_run_stats(CclArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_collect(CclArgs a, int *__restrict__ ncomp,
-                                                                  int *__restrict__ ncounted,
-                                                                  fm_component *__restrict__ comps, int maxc,
-                                                                  int min_area, int max_area) {
-    int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (warp >= a.nf * a.h) return;
-    int lf = warp / a.h, y = warp - lf * a.h;
-    int f = a.f0 + lf;
-    if (a.any && !a.any[f]) return;
+__device__ __forceinline__ void collect_row(const CclArgs &a, int lf, int f, int y, int lane) {
     int n = a.rowcnt[(size_t)lf * a.h + y];
     size_t base = (size_t)lf * a.slots + (size_t)y * a.cap;
     const int *parent = a.parent + (size_t)lf * (a.slots + 1);
     for (int i = lane; i < n; i += 32) {
         int id = 1 + y * a.cap + i;
         if (__ldcg(parent + id) != id) continue;
-        int area2 = a.area2[base + i];
+        int area2 = __ldcg(a.area2 + base + i);
         const int *bb = a.bbox + (base + i) * 4;
-        int slot = atomicAdd(ncomp + f, 1);
+        int slot = atomicAdd(a.ncomp + f, 1);
         // find_motion.py:684  `if self.max_area < area < self.min_area: continue`  (area = area2/2)
-        bool skipped = (2LL * max_area < area2) && (area2 < 2LL * min_area);
-        if (!skipped) atomicAdd(ncounted + f, 1);
-        if (slot < maxc) {
+        bool skipped = (2LL * a.max_area < area2) && (area2 < 2LL * a.min_area);
+        if (!skipped) atomicAdd(a.ncounted + f, 1);
+        if (slot < a.maxc) {
             fm_component c;
             c.area_x2 = area2;
-            c.x = bb[0]; c.y = bb[1]; c.w = bb[2] - bb[0] + 1; c.h = bb[3] - bb[1] + 1;
-            comps[(size_t)f * maxc + slot] = c;
+            int x0 = __ldcg(bb), y0 = __ldcg(bb + 1), x1 = __ldcg(bb + 2), y1 = __ldcg(bb + 3);
+            c.x = x0; c.y = y0; c.w = x1 - x0 + 1; c.h = y1 - y0 + 1;
+            a.comps[(size_t)f * a.maxc + slot] = c;
         }
     }
+}
+
+// One CTA labels one frame: seven row-parallel phases separated by block barriers (all traffic
+// between phases goes through L2: atomics and ld.global.cg).  Only the rows around the set
+// pixels are visited; quiet frames exit at once.
+#define CCL_THREADS 1024
+__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a) {
+    const int lf = blockIdx.x, f = a.f0 + lf;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
+    int ylo = 0, yhi = a.h - 1;
+    if (a.rowrange) {
+        int ymax = a.rowrange[2 * f], ymin = a.h - 1 - a.rowrange[2 * f + 1];
+        if (ymax < 0) return;                       // no set pixel in this frame
+        ylo = max(ymin - 1, 0);
+        yhi = min(ymax + 1, a.h - 1);
+    }
+    if (threadIdx.x == 0) a.parent[(size_t)lf * (a.slots + 1)] = 0;      // the outside node
+    // pass 1: background runs, 4-connected, linked to the outside -> holes
+    for (int y = ylo + warp; y <= yhi; y += nw) runs_row<true>(a, a.plane, lf, f, y, lane);
+    __syncthreads();
+    for (int y = ylo + warp; y <= yhi; y += nw) union_row<false, true>(a, lf, y, ylo, lane);
+    __syncthreads();
+    for (int y = ylo + warp; y <= yhi; y += nw) fill_row(a, lf, f, y, lane);
+    __syncthreads();
+    // pass 2: hole-filled foreground, 8-connected
+    for (int y = ylo + warp; y <= yhi; y += nw) runs_row<false>(a, a.fill, lf, f, y, lane);
+    __syncthreads();
+    for (int y = ylo + warp; y <= yhi; y += nw) union_row<true, false>(a, lf, y, ylo, lane);
+    __syncthreads();
+    for (int y = ylo + warp; y <= yhi; y += nw) stats_row(a, lf, f, y, lane);
+    __syncthreads();
+    for (int y = ylo + warp; y <= yhi; y += nw) collect_row(a, lf, f, y, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -410,34 +447,19 @@ void fm_ccl_free(CclScratch *s) {
 }
 
 // labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
-static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *any, int F, int w,
+static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
                    int max_area, int *errflag, cudaStream_t st) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
         CclArgs a;
-        a.any = any; a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
+        a.plane = plane; a.fill = fill; a.rowrange = rowrange;
+        a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
         a.bbox = sc.bbox; a.errflag = errflag;
-        int blocks = (nf * h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        int thr = 32 * WARPS_PER_BLOCK;
-        // pass 1: background, 4-connected, linked to the outside -> holes
-        a.plane = plane;
-        k_runs<true><<<blocks, thr, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
-        k_union<false, true><<<blocks, thr, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
-        k_fill_holes<<<blocks, thr, 0, st>>>(a, fill);
-        FM_LAUNCH_CHECK();
-        // pass 2: hole-filled foreground, 8-connected
-        a.plane = fill;
-        k_runs<false><<<blocks, thr, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
-        k_union<true, false><<<blocks, thr, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
-        k_run_stats<<<blocks, thr, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
-        k_collect<<<blocks, thr, 0, st>>>(a, ncomp, ncounted, comps, maxc, min_area, max_area);
+        a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
+        a.min_area = min_area; a.max_area = max_area;
+        k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a);
         FM_LAUNCH_CHECK();
     }
     return FM_OK;
@@ -445,12 +467,16 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
 
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
     const int F = c->S * T;
-    FM_CUDA(cudaMemsetAsync(c->any, 0, (size_t)F * sizeof(int), st));
+    FM_CUDA(cudaMemsetAsync(c->any, 0xFF, (size_t)F * 2 * sizeof(int), st));     // row ranges: (-1, -1)
     FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (size_t)F * sizeof(int), st));
     FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
     int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    k_dilate<<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, F, c->w, c->h, c->wpr,
-                                                     c->ntiles * FM_TILE_WORDS);
+    if (c->w % 32 == 0)
+        k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, nullptr, F, c->w, c->h,
+                                                               c->wpr, c->ntiles * FM_TILE_WORDS);
+    else
+        k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, nullptr, F, c->w, c->h,
+                                                                c->wpr, c->ntiles * FM_TILE_WORDS);
     FM_LAUNCH_CHECK();
     int rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
                      c->maxc, c->info.min_area, c->info.max_area, c->errflag, st);
@@ -484,6 +510,7 @@ int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n,
     k_u8_to_bits<<<grid, 64>>>(d8, pl, w, h, wpr);
     FM_LAUNCH_CHECK();
     rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, 0);
+    FM_CUDA(cudaDeviceSynchronize());
     if (rc) return rc;
     int hc[3];
     FM_CUDA(cudaMemcpy(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost));
