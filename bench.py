@@ -216,6 +216,21 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # libraries (NCCL's version banner, ...) write to fd 1; keep stdout clean for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
 
     import numpy as np
     import torch
@@ -316,6 +331,7 @@ def main():
         extras = secondary_regimes(args, ring_dev, torch, dist)
 
     eng.close()
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -325,9 +341,9 @@ def main():
         }
         if extras:
             line["other_regimes"] = extras
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def secondary_regimes(args, ring_dev, torch, dist):
