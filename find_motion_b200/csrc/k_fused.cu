@@ -19,11 +19,12 @@
 
 #define FT_W 128
 #define FT_H 64
-#define FG_WORDS 34        // gray words per shared row: cols x0-4 .. x0+131
+#define FG_WORDS 36        // gray words per shared row: cols x0-4 .. x0+139 (18 units of 8 pixels)
 #define FG_ROWS 68         // rows y0-2 .. y0+65
 #define FUSED_THREADS 256
-#define RAW_PITCH 416      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+399 (TMA box of 104 u32)
-#define RAW_STAGE (RAW_PITCH * FG_ROWS)
+#define RAW_PITCH 432      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+415 (TMA box of 108 u32)
+#define RAW_BYTES (RAW_PITCH * FG_ROWS)                 // bytes one TMA box delivers
+#define RAW_STAGE ((RAW_BYTES + 127) / 128 * 128)        // stage stride (TMA destinations are 128 B aligned)
 
 // ---- TMA / mbarrier primitives (sm_100a PTX) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], RAW_STAGE);
+        mbar_expect_tx(&bars[0], RAW_BYTES);
         tma_load_4d(raw, &tmap, &bars[0], cx, cy, 0, s);
     }
     uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords;
@@ -218,18 +219,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     for (int t = 0; t < p.T; t++) {
         __syncthreads();            // everyone is done with gray(t-1) and with raw stage (t+1)&1
         if (tid == 0 && t + 1 < p.T) {
-            mbar_expect_tx(&bars[(t + 1) & 1], RAW_STAGE);
+            mbar_expect_tx(&bars[(t + 1) & 1], RAW_BYTES);
             tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, t + 1, s);
         }
         mbar_wait(&bars[t & 1], (t >> 1) & 1);
         // ---- staged BGR -> gray bytes in shared memory (tile + halo), 4 pixels per unit ----
         {
+            // the staged rows are dense (pitch 432 B = 36 units of 12 B, first unit at byte 4 because the TMA box
+            // must start 16 B aligned) and so are the gray rows (36 words): unit u is raw + 4 + 12 u -> sg[u].
+            // Lanes read words 3 apart: conflict-free.
             const unsigned char *rs = raw + (t & 1) * RAW_STAGE + 4;
-#pragma unroll 3
-            for (int u = tid; u < FG_ROWS * FG_WORDS; u += FUSED_THREADS) {
-                int ry = u / FG_WORDS, ux = u - ry * FG_WORDS;
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + ry * RAW_PITCH + ux * 12);
-                sg[u] = gray4(q[0], q[1], q[2]);
+#pragma unroll
+            for (int i = 0; i < (FG_ROWS * FG_WORDS + FUSED_THREADS - 1) / FUSED_THREADS; i++) {
+                int u = tid + i * FUSED_THREADS;
+                if (u < FG_ROWS * FG_WORDS) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + u * 12);
+                    sg[u] = gray4(q[0], q[1], q[2]);
+                }
             }
         }
         __syncthreads();
