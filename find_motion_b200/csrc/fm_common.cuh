@@ -50,10 +50,11 @@ struct fm_ctx {
     int maxc;
     // tables
     int *coef;                 // [k] 8.8 fixed-point Gaussian taps
+    uint4 *etab;               // [nd] taps packed 4 per word for the four output phases (IDP.4A blur)
     ResizeTab xtab, ytab;
     // planes
     uint8_t *gray;             // [S][Tmax][h][w]
-    uint16_t *hor;             // [S][Tmax][h][w]  horizontal pass (generic blur)
+    uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or two row-quad byte planes [2][S][Tmax][hq][w] u32
     uint8_t *blur;             // [S][Tmax][h][w]  masked blur
     double *bg;                // [S][ntiles][8][32][2]  float64 background, tiled
     uint32_t *maskbits;        // [S][h][wpr]  1 = zero the blur here
@@ -122,6 +123,7 @@ int fm_launch_bg_export(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st)
 int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st);
 int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st);
 bool fm_fused_supported(const fm_ctx *c);
+int fm_blur_quads(const fm_ctx *c);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);

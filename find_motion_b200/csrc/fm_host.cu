@@ -121,7 +121,7 @@ static int upload_tab(ResizeTab *d, const HostTab &h) {
 extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
-    cudaFree(c->coef);
+    cudaFree(c->coef); cudaFree(c->etab);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
@@ -210,7 +210,26 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     }
     c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);
     inf.front_end = c->fused ? 0 : (c->resize_mode == 0 ? 1 : 2);
-    if ((rc = upload(&c->coef, gauss_coeffs(c->k)))) return fail(rc);
+    {
+        std::vector<int> taps = gauss_coeffs(c->k);
+        if ((rc = upload(&c->coef, taps))) return fail(rc);
+        // E[d][ph] byte b = c[4(d - D0) - ph + r + b]  (k_frontend.cu, wide-kernel Gaussian)
+        const int r = c->k >> 1, D0 = (r + 3) / 4 + 1, nd = 2 * D0 + 1;
+        std::vector<uint4> et(nd);
+        for (int d = 0; d < nd; d++) {
+            uint32_t e[4];
+            for (int ph = 0; ph < 4; ph++) {
+                uint32_t v = 0;
+                for (int b = 0; b < 4; b++) {
+                    int t = 4 * (d - D0) - ph + r + b;
+                    if (t >= 0 && t < c->k) v |= (uint32_t)(taps[t] & 255) << (8 * b);
+                }
+                e[ph] = v;
+            }
+            et[d] = make_uint4(e[0], e[1], e[2], e[3]);
+        }
+        if ((rc = upload(&c->etab, et))) return fail(rc);
+    }
 
     const size_t F = (size_t)c->S * c->Tmax;
     const size_t flatw = (size_t)c->ntiles * FM_TILE_WORDS;
@@ -224,7 +243,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
         }                                                                                 \
     } while (0)
     ALLOC(c->gray, F * c->N);
-    ALLOC(c->hor, F * c->N * sizeof(uint16_t));
+    ALLOC(c->hor, std::max(F * c->N * sizeof(uint16_t), 2 * F * (size_t)(fm_blur_quads(c) + 4) * c->w * sizeof(uint32_t)));
     ALLOC(c->blur, F * c->N + 64);
     const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX, c->fused ? fm_fused_bg_doubles(c) : (size_t)0);
     ALLOC(c->bg, bg_doubles * sizeof(double));
