@@ -173,6 +173,90 @@ __global__ void __launch_bounds__(K0_THREADS) k_resize_gray(K0Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0w: the same INTER_AREA + gray, one WARP per (frame, destination row), no block barriers.
+// The warp streams its source rows through a private shared-memory row buffer with 128-bit loads
+// (all loads of a row in flight together), each lane owns destination columns lane, lane+32, ... and
+// keeps their horizontal and vertical float32 chains in registers.  Used when w <= 128 (tables mode).
+// ---------------------------------------------------------------------------------------------
+#define K0W_WARPS 8
+
+// task = ((frame * h + dy) * nq + q): the warp produces destination columns q*dxw .. q*dxw+dxw-1 (one per lane)
+__global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_warp(K0Params p, int segpitch, int tasks, int nq,
+                                                                     int dxw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int task = blockIdx.x * K0W_WARPS + warp;
+    if (task >= tasks) return;
+    const int q = task % nq, fd = task / nq;
+    const int f = fd / p.h, dy = fd - f * p.h;
+    const int s = f / p.T, t = f - s * p.T;
+    const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
+    unsigned char *rowbuf = smem + (size_t)warp * segpitch;
+    const int rowbytes = p.W * 3;
+    const int y0 = p.ystart[dy], ny = p.ystart[dy + 1] - y0;
+    const int dxa = q * dxw, dxb = min(dxa + dxw, p.w);
+    const int dx = dxa + lane;
+    const bool live = lane < dxw && dx < p.w;
+    // source byte range of this warp's columns
+    const int b_lo = p.xidx[p.xstart[dxa]] * 3, b_hi = (p.xidx[p.xstart[dxb] - 1] + 1) * 3;
+    int xa = 0, xn = 0;
+    int xfirst = 0;
+    if (live) { xa = p.xstart[dx]; xn = p.xstart[dx + 1] - xa; xfirst = p.xidx[xa]; }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < ny; j++) {
+        const int sy = p.yidx[y0 + j];
+        const float beta = p.ywt[y0 + j];
+        const uint8_t *seg = src + (size_t)sy * rowbytes + b_lo;          // first needed byte
+        const int nbytes = b_hi - b_lo;
+        const int mis = (int)((uintptr_t)seg & 15);
+        const uint4 *seg16 = reinterpret_cast<const uint4 *>(seg - mis);
+        const int n16 = (mis + nbytes + 15) >> 4;
+        uint4 *dst16 = reinterpret_cast<uint4 *>(rowbuf);
+        // 16-byte blocks that are not fully inside the ROW are fetched bytewise (nothing outside the
+        // caller's buffer is touched)
+        const long row_lo = -(long)b_lo + mis, row_hi = (long)rowbytes - b_lo + mis;   // row extent in buffer coords
+        __syncwarp();
+        for (int i = lane; i < n16; i += 32) {
+            long o0 = (long)i * 16;
+            if (o0 >= row_lo && o0 + 16 <= row_hi) {
+                dst16[i] = __ldg(seg16 + i);
+            } else {
+                unsigned char *d = reinterpret_cast<unsigned char *>(dst16 + i);
+                for (int b = 0; b < 16; b++) {
+                    long o = o0 + b;
+                    d[b] = (o >= row_lo && o < row_hi) ? seg[o - mis] : 0;
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned char *rb = rowbuf + mis - b_lo;                    // rb[3*x + c] = source pixel x
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        const unsigned char *px = rb + xfirst * 3;      // the taps of a column are consecutive source pixels
+        const float *wt = p.xwt + xa;
+#pragma unroll 4
+        for (int qq = 0; qq < xn; qq++, px += 3) {
+            const float al = __ldg(wt + qq);
+            b0 = __fadd_rn(b0, __fmul_rn((float)px[0], al));
+            b1 = __fadd_rn(b1, __fmul_rn((float)px[1], al));
+            b2 = __fadd_rn(b2, __fmul_rn((float)px[2], al));
+        }
+        if (j == 0) {
+            s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+            s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+            s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+        }
+    }
+    if (live) {
+        int v0 = min(max(__float2int_rn(s0), 0), 255);
+        int v1 = min(max(__float2int_rn(s1), 0), 255);
+        int v2 = min(max(__float2int_rn(s2), 0), 255);
+        p.gray[((size_t)f * p.h + dy) * p.w + dx] = (uint8_t)fm_gray(v0, v1, v2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic separable Gaussian, two passes through a u16 plane.
 // This is the fallback for wide kernels; the fused kernel (k_fused.cu) covers small k.
 // ---------------------------------------------------------------------------------------------
@@ -394,19 +478,34 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         p.max_ytaps = c->resize_mode == 1 ? c->ytab.max_taps : c->fy;
         p.gray = c->gray;
         int rowpitch = (c->W * 3 + 16 + 15) & ~15;
-        size_t smem = (size_t)K0_GROUPS * rowpitch + (size_t)p.max_ytaps * c->w * 3 * sizeof(float);
-        if (smem > 220 * 1024) {
-            fm_set_error("resize front end needs %zu bytes of shared memory (frame too wide / ratio too large)", smem);
-            return FM_ERANGE;
+        if (c->resize_mode == 1) {
+            // one warp per (frame, destination row, group of <= 32 destination columns)
+            int nq = (c->w + 31) / 32, dxw = (c->w + nq - 1) / nq;
+            int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 2) + 32 + 15) & ~15;
+            size_t smemw = (size_t)K0W_WARPS * segpitch;
+            static size_t configured_w = 0;
+            if (smemw > configured_w) {
+                FM_CUDA(cudaFuncSetAttribute(k_resize_gray_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                configured_w = smemw;
+            }
+            int tasks = c->h * F * nq;
+            k_resize_gray_warp<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
+            FM_LAUNCH_CHECK();
+        } else {
+            size_t smem = (size_t)K0_GROUPS * rowpitch + (size_t)p.max_ytaps * c->w * 3 * sizeof(float);
+            if (smem > 220 * 1024) {
+                fm_set_error("resize front end needs %zu bytes of shared memory (frame too wide / ratio too large)", smem);
+                return FM_ERANGE;
+            }
+            static size_t configured = 0;
+            if (smem > configured) {
+                FM_CUDA(cudaFuncSetAttribute(k_resize_gray, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            dim3 grid(c->h, F);
+            k_resize_gray<<<grid, K0_THREADS, smem, st>>>(p);
+            FM_LAUNCH_CHECK();
         }
-        static size_t configured = 0;
-        if (smem > configured) {
-            FM_CUDA(cudaFuncSetAttribute(k_resize_gray, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        dim3 grid(c->h, F);
-        k_resize_gray<<<grid, K0_THREADS, smem, st>>>(p);
-        FM_LAUNCH_CHECK();
     }
     // separable blur
     if (c->k >= 3 && (c->w % 4) == 0) {
