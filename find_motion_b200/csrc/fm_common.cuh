@@ -52,6 +52,8 @@ struct fm_ctx {
     int *coef;                 // [k] 8.8 fixed-point Gaussian taps
     uint4 *etab;               // [nd] taps packed 4 per word for the four output phases (IDP.4A blur)
     ResizeTab xtab, ytab;
+    int *g4start, *g4n, *g4off;   // x taps regrouped in 4-pixel groups with zero-weight padding (k_resize_gray_g4)
+    float4 *g4w;
     // planes
     uint8_t *gray;             // [S][Tmax][h][w]
     uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or two row-quad byte planes [2][S][Tmax][hq][w] u32

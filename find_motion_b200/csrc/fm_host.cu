@@ -122,6 +122,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
     cudaFree(c->coef); cudaFree(c->etab);
+    cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
@@ -204,7 +205,30 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
             c->resize_mode = 2; c->fx = isx; c->fy = isy;
         } else {
             c->resize_mode = 1;
-            if ((rc = upload_tab(&c->xtab, area_tab(c->W, c->w)))) return fail(rc);
+            HostTab xt = area_tab(c->W, c->w);
+            if ((rc = upload_tab(&c->xtab, xt))) return fail(rc);
+            {   // the same x taps in groups of 4 consecutive source pixels, zero-weight padded
+                std::vector<int> g4s(c->w), g4n(c->w), g4o(c->w);
+                std::vector<float4> g4w;
+                for (int dx = 0; dx < c->w; dx++) {
+                    int a = xt.start[dx], b = xt.start[dx + 1];
+                    int first = xt.idx[a], last = xt.idx[b - 1];
+                    int gs = first & ~3, ge = (last | 3) + 1;
+                    g4s[dx] = gs; g4n[dx] = (ge - gs) / 4; g4o[dx] = (int)g4w.size();
+                    for (int g = gs; g < ge; g += 4) {
+                        float wv[4];
+                        for (int i = 0; i < 4; i++) {
+                            int x = g + i;
+                            wv[i] = (x >= first && x <= last) ? xt.wt[a + (x - first)] : 0.0f;
+                        }
+                        g4w.push_back(make_float4(wv[0], wv[1], wv[2], wv[3]));
+                    }
+                }
+                if ((rc = upload(&c->g4start, g4s))) return fail(rc);
+                if ((rc = upload(&c->g4n, g4n))) return fail(rc);
+                if ((rc = upload(&c->g4off, g4o))) return fail(rc);
+                if ((rc = upload(&c->g4w, g4w))) return fail(rc);
+            }
             if ((rc = upload_tab(&c->ytab, area_tab(c->H, c->h)))) return fail(rc);
         }
     }

@@ -256,6 +256,102 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_warp(K0Params p,
     }
 }
 
+// Same decomposition for 4-byte aligned rows: every lane walks its taps in groups of 4 source pixels
+// (12 bytes = three aligned 32-bit shared loads), the tap list padded to group boundaries with zero
+// weights (x + 0*y == x exactly, so the strictly ordered float32 chains are unchanged).  Bytes become
+// floats with PRMT into the mantissa of 2^23 and one FADD -- no byte loads, no XU conversions.
+__device__ __forceinline__ float byte_f32(uint32_t w, int i) {
+    return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)i)), -8388608.0f);
+}
+
+struct K0GParams {
+    const int *g4start;      // [w] first source pixel of the column's first group (multiple of 4)
+    const int *g4n;          // [w] groups
+    const int *g4off;        // [w] offset (in float4) into g4w
+    const float4 *g4w;       // padded weights
+};
+
+__global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K0GParams gp, int segpitch, int tasks,
+                                                                   int nq, int dxw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int task = blockIdx.x * K0W_WARPS + warp;
+    if (task >= tasks) return;
+    const int q = task % nq, fd = task / nq;
+    const int f = fd / p.h, dy = fd - f * p.h;
+    const int s = f / p.T, t = f - s * p.T;
+    const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
+    unsigned char *rowbuf = smem + (size_t)warp * segpitch;
+    const int rowbytes = p.W * 3;
+    const int y0 = p.ystart[dy], ny = p.ystart[dy + 1] - y0;
+    const int dxa = q * dxw, dxb = min(dxa + dxw, p.w);
+    const int dx = dxa + lane;
+    const bool live = lane < dxw && dx < p.w;
+    const int b_lo = gp.g4start[dxa] * 3;
+    const int b_hi = min((gp.g4start[dxb - 1] + 4 * gp.g4n[dxb - 1]) * 3, rowbytes);
+    int gs = 0, gn = 0;
+    const float4 *gw = gp.g4w;
+    if (live) { gs = gp.g4start[dx]; gn = gp.g4n[dx]; gw += gp.g4off[dx]; }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < ny; j++) {
+        const int sy = p.yidx[y0 + j];
+        const float beta = p.ywt[y0 + j];
+        const uint8_t *seg = src + (size_t)sy * rowbytes + b_lo;
+        const int nbytes = b_hi - b_lo;
+        const int mis = (int)((uintptr_t)seg & 15);
+        const uint4 *seg16 = reinterpret_cast<const uint4 *>(seg - mis);
+        const int n16 = (mis + nbytes + 15) >> 4;
+        uint4 *dst16 = reinterpret_cast<uint4 *>(rowbuf);
+        const long row_lo = -(long)b_lo + mis, row_hi = (long)rowbytes - b_lo + mis;
+        __syncwarp();
+        for (int i = lane; i < n16; i += 32) {
+            long o0 = (long)i * 16;
+            if (o0 >= row_lo && o0 + 16 <= row_hi) {
+                dst16[i] = __ldg(seg16 + i);
+            } else {
+                unsigned char *d = reinterpret_cast<unsigned char *>(dst16 + i);
+                for (int b = 0; b < 16; b++) {
+                    long o = o0 + b;
+                    d[b] = (o >= row_lo && o < row_hi) ? seg[o - mis] : 0;
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(rowbuf + mis - b_lo + 3 * gs);
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll 2
+        for (int g = 0; g < gn; g++) {
+            const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
+            const float4 a = __ldg(gw + g);
+            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W0, 0), a.x));
+            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W0, 1), a.x));
+            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W0, 2), a.x));
+            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W0, 3), a.y));
+            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W1, 0), a.y));
+            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W1, 1), a.y));
+            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W1, 2), a.z));
+            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W1, 3), a.z));
+            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W2, 0), a.z));
+            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W2, 1), a.w));
+            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W2, 2), a.w));
+            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W2, 3), a.w));
+        }
+        if (j == 0) {
+            s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+            s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+            s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+        }
+    }
+    if (live) {
+        int v0 = min(max(__float2int_rn(s0), 0), 255);
+        int v1 = min(max(__float2int_rn(s1), 0), 255);
+        int v2 = min(max(__float2int_rn(s2), 0), 255);
+        p.gray[((size_t)f * p.h + dy) * p.w + dx] = (uint8_t)fm_gray(v0, v1, v2);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // generic separable Gaussian, two passes through a u16 plane.
 // This is the fallback for wide kernels; the fused kernel (k_fused.cu) covers small k.
@@ -481,7 +577,7 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         if (c->resize_mode == 1) {
             // one warp per (frame, destination row, group of <= 32 destination columns)
             int nq = (c->w + 31) / 32, dxw = (c->w + nq - 1) / nq;
-            int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 2) + 32 + 15) & ~15;
+            int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 10) + 32 + 15) & ~15;
             size_t smemw = (size_t)K0W_WARPS * segpitch;
             static size_t configured_w = 0;
             if (smemw > configured_w) {
@@ -489,7 +585,19 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                 configured_w = smemw;
             }
             int tasks = c->h * F * nq;
-            k_resize_gray_warp<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
+            const bool aligned4 = ((((uintptr_t)frames) | sstride | fstride | ((size_t)c->W * 3)) & 3) == 0;
+            if (aligned4 && c->g4w) {
+                static size_t configured_g = 0;
+                if (smemw > configured_g) {
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    configured_g = smemw;
+                }
+                K0GParams gp;
+                gp.g4start = c->g4start; gp.g4n = c->g4n; gp.g4off = c->g4off; gp.g4w = c->g4w;
+                k_resize_gray_g4<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+            } else {
+                k_resize_gray_warp<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
+            }
             FM_LAUNCH_CHECK();
         } else {
             size_t smem = (size_t)K0_GROUPS * rowpitch + (size_t)p.max_ytaps * c->w * 3 * sizeof(float);
