@@ -25,7 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
-METRIC = "1080p frames/sec (whole box)"
+METRIC = "1080p frames/sec (whole box)"   # other --size values are characterisation runs
 
 
 def parse_args():
@@ -42,6 +42,10 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=16, help="T: frames per stream per step")
     ap.add_argument("--ring", type=int, default=32, help="frames per stream resident in HBM")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--size", default="1920x1080", help="frame size WxH (the headline metric is 1080p)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic clips (0 = one per stream); "
+                    "streams reuse them round-robin (large-batch sweeps)")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary regimes (k=97, default mode)")
     return ap.parse_args()
@@ -167,7 +171,7 @@ def probe_info(kw):
 
 def workload_config(args, kw, info):
     return {
-        "workload": f"BASELINE configs[1]/[2]: {args.streams} x 1080p30 synthetic streams per GPU "
+        "workload": f"BASELINE configs[1]/[2]: {args.streams} x {W}x{H} synthetic streams per GPU "
                     f"({args.streams * args.gpus} in the job; 64 at 8 GPUs = configs[2]), CFG2 polygon masks "
                     f"(README square+triangle + translated pair), min-time/cache-time logic, "
                     f"{'full-resolution' if args.mode == 'full' else 'reference-default'} mode",
@@ -213,7 +217,9 @@ def time_engine(eng, ring_dev, args, torch, dist, world):
 
 
 def main():
+    global W, H
     args = parse_args()
+    W, H = (int(v) for v in args.size.lower().split("x"))
     if args.impl == "reference":
         return run_reference(args)
     # libraries (NCCL's version banner, ...) write to fd 1; keep stdout clean for the ONE JSON line
@@ -260,11 +266,20 @@ def run_b200(args):
             cpu = {"error": str(e)[:200]}
 
     # synthetic streams: seed = 1000*cfg + global stream id, resident in HBM
-    ring_host = torch.empty((S, R, H, W, 3), dtype=torch.uint8).pin_memory()
-    for s in range(S):
-        clip = synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + s), script=bench_script(R))
-        ring_host[s] = torch.from_numpy(clip)
-    ring_dev = ring_host.cuda(non_blocking=True)
+    nd = min(S, args.distinct) if args.distinct else S
+    if nd == S:
+        ring_host = torch.empty((S, R, H, W, 3), dtype=torch.uint8).pin_memory()
+        for s in range(S):
+            clip = synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + s), script=bench_script(R))
+            ring_host[s] = torch.from_numpy(clip)
+        ring_dev = ring_host.cuda(non_blocking=True)
+    else:
+        ring_host = None
+        ring_dev = torch.empty((S, R, H, W, 3), dtype=torch.uint8, device="cuda")
+        for d in range(nd):
+            clip = torch.from_numpy(synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + d), script=bench_script(R))).cuda()
+            for s in range(d, S, nd):
+                ring_dev[s] = clip
     torch.cuda.synchronize()
 
     eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **kw)
@@ -308,6 +323,9 @@ def run_b200(args):
     # end to end through the host-buffer entry point
     eng.timing(enable=False)
     eng.reset()
+    if args.no_e2e or ring_host is None:
+        e2e = None
+        return finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, {})
     host_batch = [ring_host[:, a:a + T] for a in range(0, R, T)]
     for i in range(2):
         eng.process_host(host_batch[i % len(host_batch)])
@@ -329,12 +347,15 @@ def run_b200(args):
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras = secondary_regimes(args, ring_dev, torch, dist)
+    return finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, extras)
 
+
+def finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, extras):
     eng.close()
     line = None
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (W, H) == (1920, 1080) else f"{W}x{H} frames/sec (whole box)", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "config": workload_config(args, kw, info),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -266,9 +266,12 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
             return fail(FM_ENOMEM);                                                       \
         }                                                                                 \
     } while (0)
-    ALLOC(c->gray, F * c->N);
-    ALLOC(c->hor, std::max(F * c->N * sizeof(uint16_t), 2 * F * (size_t)(fm_blur_quads(c) + 4) * c->w * sizeof(uint32_t)));
-    ALLOC(c->blur, F * c->N + 64);
+    // the fused front end never materialises gray / horizontal / blur planes (except as parity taps)
+    const bool need_planes = !c->fused || (cfg->flags & FM_FLAG_KEEP_PLANES);
+    const bool need_hor = !c->fused;
+    ALLOC(c->gray, need_planes ? F * c->N : 16);
+    ALLOC(c->hor, !need_hor ? 16 : std::max(F * c->N * sizeof(uint16_t), 2 * F * (size_t)(fm_blur_quads(c) + 4) * c->w * sizeof(uint32_t)));
+    ALLOC(c->blur, need_planes ? F * c->N + 64 : 64);
     const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX, c->fused ? fm_fused_bg_doubles(c) : (size_t)0);
     ALLOC(c->bg, bg_doubles * sizeof(double));
     ALLOC(c->maskbits, (size_t)c->S * c->h * c->wpr * 4);
