@@ -317,8 +317,9 @@ __device__ __forceinline__ void collect_row(const CclArgs &a, int lf, int f, int
 // between phases goes through L2: atomics and ld.global.cg).  Only the rows around the set
 // pixels are visited; quiet frames exit at once.
 #define CCL_THREADS 1024
-__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a) {
+__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const int *__restrict__ heavy) {
     const int lf = blockIdx.x, f = a.f0 + lf;
+    if (heavy && !heavy[f]) return;                 // already labelled by k_ccl_frame_smem
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
     int ylo = 0, yhi = a.h - 1;
     if (a.rowrange) {
@@ -343,6 +344,325 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a) {
     for (int y = ylo + warp; y <= yhi; y += nw) stats_row(a, lf, f, y, lane);
     __syncthreads();
     for (int y = ylo + warp; y <= yhi; y += nw) collect_row(a, lf, f, y, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: the same labelling with the run table and the union-find forest in SHARED memory.
+// Frames whose active rows hold more than CCL2_CAP runs (or planes wider than 4096 px) are flagged
+// "heavy" and left to k_ccl_frame.  All dependent accesses (binary searches over the previous row's
+// runs, find / union pointer chasing) stay on chip; global memory is touched only to stream the bit
+// planes (two rows per warp iteration so that their loads overlap) and for the per-root reductions.
+// ---------------------------------------------------------------------------------------------
+#define CCL2_THREADS 512
+#define CCL2_WARPS (CCL2_THREADS / 32)
+#define CCL2_CAP 10240
+#define CCL2_K 4                 // words per lane: planes up to 4096 px wide
+
+struct Ccl2Smem {
+    int *rowoff;      // [rows + 1] exclusive prefix of the per-row run counts (current pass)
+    int *rowoff2;     // [rows + 1] same for the second pass
+    int *parent;      // [CCL2_CAP + 1], id 0 = outside
+    uint16_t *xs, *xe;
+};
+
+template <bool INVERT>
+__device__ __forceinline__ void row_words(const uint32_t *row, int w, int wpr, int lane, uint32_t (&B)[CCL2_K]) {
+#pragma unroll
+    for (int k = 0; k < CCL2_K; k++) B[k] = plane_word<INVERT>(row, lane + 32 * k, w, wpr);
+}
+
+__device__ __forceinline__ void row_starts_ends(const uint32_t (&B)[CCL2_K], int lane, uint32_t (&S)[CCL2_K],
+                                                uint32_t (&E)[CCL2_K]) {
+#pragma unroll
+    for (int k = 0; k < CCL2_K; k++) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, B[k], 1), dn = __shfl_down_sync(0xffffffffu, B[k], 1);
+        uint32_t cp = k > 0 ? __shfl_sync(0xffffffffu, B[k > 0 ? k - 1 : 0], 31) : 0u;
+        uint32_t cn = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, B[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
+        uint32_t Bp = lane ? up : cp, Bn = lane < 31 ? dn : cn;
+        S[k] = B[k] & ~((B[k] << 1) | (Bp >> 31));
+        E[k] = B[k] & ~((B[k] >> 1) | (Bn << 31));
+    }
+}
+
+__device__ __forceinline__ int row_count(const uint32_t (&S)[CCL2_K]) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CCL2_K; k++) c += __popc(S[k]);
+    return __reduce_add_sync(0xffffffffu, c);
+}
+
+// write the runs of one row into the shared run table starting at slot `off`
+__device__ __forceinline__ void row_extract(const uint32_t (&S)[CCL2_K], const uint32_t (&E)[CCL2_K], int lane, int off,
+                                            const Ccl2Smem &sm) {
+    int base = off, ebase = off;       // a run may start in one 1024-px group and end in the next
+#pragma unroll
+    for (int k = 0; k < CCL2_K; k++) {
+        uint32_t s = S[k], e = E[k];
+        if (!__any_sync(0xffffffffu, (s | e) != 0)) continue;
+        int cs = __popc(s), ce = __popc(e), ps = cs, pe = ce;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int vs = __shfl_up_sync(0xffffffffu, ps, o), ve = __shfl_up_sync(0xffffffffu, pe, o);
+            if (lane >= o) { ps += vs; pe += ve; }
+        }
+        int is = base + ps - cs, ie = ebase + pe - ce;
+        const int x0 = 32 * (lane + 32 * k);
+        while (s) {
+            int bit = __ffs(s) - 1;
+            s &= s - 1;
+            sm.xs[is] = (uint16_t)(x0 + bit);
+            sm.parent[1 + is] = 1 + is;
+            is++;
+        }
+        while (e) {
+            int bit = __ffs(e) - 1;
+            e &= e - 1;
+            sm.xe[ie] = (uint16_t)(x0 + bit);
+            ie++;
+        }
+        base += __shfl_sync(0xffffffffu, ps, 31);
+        ebase += __shfl_sync(0xffffffffu, pe, 31);
+    }
+}
+
+__device__ __forceinline__ int suf_find(int *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        int gp = parent[p];
+        if (gp != p) atomicMin(parent + x, gp);      // path halving
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void suf_union(int *parent, int a, int b) {
+    while (true) {
+        a = suf_find(parent, a);
+        b = suf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+template <bool CONN8, bool OUTSIDE>
+__device__ __forceinline__ void srow_union(const Ccl2Smem &sm, const int *rowoff, int yr, int y, int w, int h, int lane) {
+    const int o0 = rowoff[yr], n = rowoff[yr + 1] - o0;
+    if (n == 0) return;
+    const int p0 = yr > 0 ? rowoff[yr - 1] : 0, np = yr > 0 ? o0 - p0 : 0;
+    const int d = CONN8 ? 1 : 0;
+    for (int i = lane; i < n; i += 32) {
+        const int xs = sm.xs[o0 + i], xe = sm.xe[o0 + i], id = 1 + o0 + i;
+        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(sm.parent, id, 0);
+        if (np) {
+            int lo = 0, hi = np;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)sm.xe[p0 + mid] < xs - d) lo = mid + 1; else hi = mid;
+            }
+            for (int q = lo; q < np && (int)sm.xs[p0 + q] <= xe + d; q++) suf_union(sm.parent, id, 1 + p0 + q);
+        }
+    }
+}
+
+// block-wide exclusive scan of cnt[0..n) in place (cnt[n] = total); n <= a few thousand
+__device__ __forceinline__ void block_scan(int *cnt, int n, int *carry_smem) {
+    // warp 0 walks the array 32 entries at a time
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int run = 0;
+        for (int b = 0; b <= n; b += 32) {
+            int i = b + lane;
+            int v = i < n ? cnt[i] : 0, inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (i <= n) cnt[i] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) *carry_smem = run;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const int lf = blockIdx.x, f = a.f0 + lf;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ylo = 0, yhi = a.h - 1;
+    if (a.rowrange) {
+        int ymax = a.rowrange[2 * f], ymin = a.h - 1 - a.rowrange[2 * f + 1];
+        if (ymax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
+        ylo = max(ymin - 1, 0);
+        yhi = min(ymax + 1, a.h - 1);
+    }
+    const int nrows = yhi - ylo + 1;
+    Ccl2Smem sm;
+    sm.rowoff = reinterpret_cast<int *>(csm);
+    sm.rowoff2 = sm.rowoff + (a.h + 2);
+    sm.parent = sm.rowoff2 + (a.h + 2);
+    sm.xs = reinterpret_cast<uint16_t *>(sm.parent + CCL2_CAP + 2);
+    sm.xe = sm.xs + CCL2_CAP;
+    __shared__ int total;
+    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr;
+    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr;
+
+    // ---- pass 1 (background, 4-connected): count, scan, extract, union ----
+    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {          // two rows in flight per warp
+        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
+        const int yr1 = yr + CCL2_WARPS;
+        row_words<true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
+        if (yr1 < nrows) row_words<true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
+        row_starts_ends(B0, lane, S, E);
+        int c = row_count(S);
+        if (lane == 0) sm.rowoff[yr] = c;
+        if (yr1 < nrows) {
+            row_starts_ends(B1, lane, S, E);
+            c = row_count(S);
+            if (lane == 0) sm.rowoff[yr1] = c;
+        }
+    }
+    __syncthreads();
+    block_scan(sm.rowoff, nrows, &total);
+    if (total > CCL2_CAP) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    if (threadIdx.x == 0) { heavy[f] = 0; sm.parent[0] = 0; }
+    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {
+        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
+        const int yr1 = yr + CCL2_WARPS;
+        row_words<true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
+        if (yr1 < nrows) row_words<true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
+        row_starts_ends(B0, lane, S, E);
+        row_extract(S, E, lane, sm.rowoff[yr], sm);
+        if (yr1 < nrows) {
+            row_starts_ends(B1, lane, S, E);
+            row_extract(S, E, lane, sm.rowoff[yr1], sm);
+        }
+    }
+    __syncthreads();
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(sm, sm.rowoff, yr, ylo + yr, a.w, a.h, lane);
+    __syncthreads();
+    // ---- holes -> filled plane; count the foreground runs of the filled rows ----
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
+        uint32_t F[CCL2_K], S[CCL2_K], E[CCL2_K];
+        row_words<false>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, F);
+        const int o0 = sm.rowoff[yr], n = sm.rowoff[yr + 1] - o0;
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            bool hole = false;
+            int xs = 0, xe = 0;
+            if (i < n) { hole = suf_find(sm.parent, 1 + o0 + i) != 0; xs = sm.xs[o0 + i]; xe = sm.xe[o0 + i]; }
+            uint32_t hm = __ballot_sync(0xffffffffu, hole);
+            while (hm) {
+                const int src = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int hxs = __shfl_sync(0xffffffffu, xs, src), hxe = __shfl_sync(0xffffffffu, xe, src);
+#pragma unroll
+                for (int k = 0; k < CCL2_K; k++) {
+                    const int x0 = 32 * (lane + 32 * k);
+                    int lo = max(hxs - x0, 0), hi = min(hxe - x0, 31);
+                    if (lo <= hi) F[k] |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CCL2_K; k++)
+            if (lane + 32 * k < a.wpr) fil[(size_t)(ylo + yr) * a.wpr + lane + 32 * k] = F[k];
+        row_starts_ends(F, lane, S, E);
+        const int c = row_count(S);
+        if (lane == 0) sm.rowoff2[yr] = c;
+    }
+    __syncthreads();
+    block_scan(sm.rowoff2, nrows, &total);
+    if (total > CCL2_CAP) { if (threadIdx.x == 0) heavy[f] = 1; return; }     // (cannot exceed pass 1 by much; be safe)
+    // ---- pass 2 (filled foreground, 8-connected) ----
+    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {
+        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
+        const int yr1 = yr + CCL2_WARPS;
+        row_words<false>(fil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
+        if (yr1 < nrows) row_words<false>(fil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
+        row_starts_ends(B0, lane, S, E);
+        row_extract(S, E, lane, sm.rowoff2[yr], sm);
+        if (yr1 < nrows) {
+            row_starts_ends(B1, lane, S, E);
+            row_extract(S, E, lane, sm.rowoff2[yr1], sm);
+        }
+    }
+    __syncthreads();
+    // per-root accumulators live in the global scratch, indexed by the compact run id
+    int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        area2[i] = 0;
+        reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
+    }
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(sm, sm.rowoff2, yr, ylo + yr, a.w, a.h, lane);
+    __syncthreads();
+    // ---- per-run bit-quad area and bounding box -> root ----
+    // The 2x2-window masks of a row pair are computed word-parallel (lanes hold the words of rows y-1 and y),
+    // parked in the warp's shared scratch, and each run then sums the windows x in [xs-1, xe] it owns.
+    uint32_t *q4s = reinterpret_cast<uint32_t *>(sm.xe + CCL2_CAP) + warp * (2 * 32 * CCL2_K);
+    uint32_t *q3s = q4s + 32 * CCL2_K;
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
+        const int y = ylo + yr;
+        const int o0 = sm.rowoff2[yr], n = sm.rowoff2[yr + 1] - o0;
+        if (n == 0) continue;
+        const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
+        if (has_up) {
+            uint32_t L[CCL2_K], U[CCL2_K];
+            row_words<false>(fil + (size_t)y * a.wpr, a.w, a.wpr, lane, L);
+            row_words<false>(fil + (size_t)(y - 1) * a.wpr, a.w, a.wpr, lane, U);
+#pragma unroll
+            for (int k = 0; k < CCL2_K; k++) {
+                uint32_t ln = __shfl_down_sync(0xffffffffu, L[k], 1), un = __shfl_down_sync(0xffffffffu, U[k], 1);
+                uint32_t lc = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, L[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
+                uint32_t uc = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, U[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
+                if (lane == 31) { ln = lc; un = uc; }
+                const uint32_t l0 = L[k], l1 = (L[k] >> 1) | (ln << 31), u0 = U[k], u1 = (U[k] >> 1) | (un << 31);
+                q4s[lane + 32 * k] = l0 & l1 & u0 & u1;
+                q3s[lane + 32 * k] = (l0 & l1 & (u0 ^ u1)) | (u0 & u1 & (l0 ^ l1));
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const int xs = sm.xs[o0 + i], xe = sm.xe[o0 + i];
+            const int root = suf_find(sm.parent, 1 + o0 + i) - 1;
+            int q = 0;
+            if (has_up) {
+                const int x0 = max(xs - 1, 0), x1 = xe;         // windows owned by this run
+                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
+                    int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
+                    uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    q += 2 * __popc(q4s[j] & m) + __popc(q3s[j] & m);
+                }
+            }
+            if (q) atomicAdd(area2 + root, q);
+            int *bb = bbox + (size_t)root * 4;
+            atomicMin(bb + 0, xs);
+            atomicMin(bb + 1, y);
+            atomicMax(bb + 2, xe);
+            atomicMax(bb + 3, y);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- roots -> component records ----
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        if (sm.parent[1 + i] != 1 + i) continue;
+        const int ar = __ldcg(area2 + i);
+        const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
+        const int slot = atomicAdd(a.ncomp + f, 1);
+        const bool skipped = (2LL * a.max_area < ar) && (ar < 2LL * a.min_area);   // find_motion.py:684
+        if (!skipped) atomicAdd(a.ncounted + f, 1);
+        if (slot < a.maxc) {
+            fm_component c;
+            c.area_x2 = ar; c.x = bb.x; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
+            a.comps[(size_t)f * a.maxc + slot] = c;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,7 +769,7 @@ void fm_ccl_free(CclScratch *s) {
 // labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
 static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
-                   int max_area, int *errflag, cudaStream_t st) {
+                   int max_area, int *errflag, int *heavy, cudaStream_t st) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
         CclArgs a;
@@ -459,8 +779,22 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.bbox = sc.bbox; a.errflag = errflag;
         a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
         a.min_area = min_area; a.max_area = max_area;
-        k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a);
-        FM_LAUNCH_CHECK();
+        if (wpr <= 32 * CCL2_K && heavy) {
+            size_t smem = (size_t)(2 * (h + 2) + CCL2_CAP + 2) * sizeof(int) + (size_t)2 * CCL2_CAP * sizeof(uint16_t) +
+                          (size_t)CCL2_WARPS * 2 * 32 * CCL2_K * sizeof(uint32_t);
+            static size_t configured = 0;
+            if (smem > configured) {
+                FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            FM_LAUNCH_CHECK();
+            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
+            FM_LAUNCH_CHECK();
+        } else {
+            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, nullptr);
+            FM_LAUNCH_CHECK();
+        }
     }
     return FM_OK;
 }
@@ -479,7 +813,7 @@ int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats
                                                                 c->wpr, c->ntiles * FM_TILE_WORDS);
     FM_LAUNCH_CHECK();
     int rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                     c->maxc, c->info.min_area, c->info.max_area, c->errflag, st);
+                     c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, st);
     if (rc) return rc;
     k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(c->state, c->ncomp, c->ncounted, c->stats, stats_out, c->S, T,
                                                  c->info.cache_frames, c->info.min_movement_frames);
@@ -502,14 +836,14 @@ int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n,
     FM_CUDA(cudaMalloc(&d8, (size_t)w * h));
     FM_CUDA(cudaMalloc(&pl, (size_t)wpr * h * 4));
     FM_CUDA(cudaMalloc(&fill, (size_t)wpr * h * 4));
-    FM_CUDA(cudaMalloc(&cnt, 3 * sizeof(int)));
+    FM_CUDA(cudaMalloc(&cnt, 4 * sizeof(int)));
     FM_CUDA(cudaMalloc(&comps, (size_t)maxc * sizeof(fm_component)));
     FM_CUDA(cudaMemcpy(d8, plane_host, (size_t)w * h, cudaMemcpyHostToDevice));
-    FM_CUDA(cudaMemset(cnt, 0, 3 * sizeof(int)));
+    FM_CUDA(cudaMemset(cnt, 0, 4 * sizeof(int)));
     dim3 grid((wpr + 63) / 64, h);
     k_u8_to_bits<<<grid, 64>>>(d8, pl, w, h, wpr);
     FM_LAUNCH_CHECK();
-    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, 0);
+    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, cnt + 3, 0);
     FM_CUDA(cudaDeviceSynchronize());
     if (rc) return rc;
     int hc[3];

@@ -100,6 +100,23 @@ def test_contours_structured_planes():
     assert label_components(full) == R.external_components(full)
 
 
+def test_contours_heavy_planes_use_the_global_fallback():
+    """More runs than the shared-memory run table holds (10240): the global-memory kernel takes over."""
+    from find_motion_b200.engine import label_components
+    from oracle import restated as R
+    rng = np.random.default_rng(13)
+    t = (rng.random((300, 1024)) < 0.35).astype(np.uint8) * 255       # ~70k runs
+    assert label_components(t, max_n=200000) == R.external_components(t)
+    stripes = np.zeros((220, 2048), np.uint8)
+    stripes[:, ::2] = 255                                              # 1024 runs per row
+    stripes[100:120, :] = 255
+    assert label_components(stripes, max_n=200000) == R.external_components(stripes)
+    wide = np.zeros((40, 5000), np.uint8)                              # wider than 4096 px: global kernel only
+    wide[5:30, 100:4900] = 255
+    wide[10:20, 2000:3000] = 0
+    assert label_components(wide) == R.external_components(wide)
+
+
 def test_mask_raster_random_polygons():
     from find_motion_b200.engine import MotionEngine
     from oracle import restated as R
