@@ -347,56 +347,62 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const i
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: the same labelling with the run table and the union-find forest in SHARED memory.
+// K2: the same labelling with the run tables and the union-find forests in SHARED memory.
 // Frames whose active rows hold more than CCL2_CAP runs (or planes wider than 4096 px) are flagged
 // "heavy" and left to k_ccl_frame.  All dependent accesses (binary searches over the previous row's
 // runs, find / union pointer chasing) stay on chip; global memory is touched only to stream the bit
-// planes (two rows per warp iteration so that their loads overlap) and for the per-root reductions.
+// planes and for the per-root reductions.  Rows get their slots in the run tables from a shared
+// cursor (atomicAdd per row), so there is no counting pass and no prefix scan; the filled plane and
+// the foreground runs are produced in the same sweep that detects the holes.
 // ---------------------------------------------------------------------------------------------
-#define CCL2_THREADS 512
+#define CCL2_THREADS 1024
 #define CCL2_WARPS (CCL2_THREADS / 32)
-#define CCL2_CAP 10240
-#define CCL2_K 4                 // words per lane: planes up to 4096 px wide
+#define CCL2_CAP 4096
 
-struct Ccl2Smem {
-    int *rowoff;      // [rows + 1] exclusive prefix of the per-row run counts (current pass)
-    int *rowoff2;     // [rows + 1] same for the second pass
-    int *parent;      // [CCL2_CAP + 1], id 0 = outside
+struct RunTable {
+    int2 *row;        // [rows] (first slot, run count) of each row
+    int *parent;      // [CCL2_CAP + 1]; for the background table id 0 = outside
     uint16_t *xs, *xe;
 };
 
-template <bool INVERT>
-__device__ __forceinline__ void row_words(const uint32_t *row, int w, int wpr, int lane, uint32_t (&B)[CCL2_K]) {
+template <int K, bool INVERT>
+__device__ __forceinline__ void row_words(const uint32_t *row, int w, int wpr, int lane, uint32_t (&B)[K]) {
 #pragma unroll
-    for (int k = 0; k < CCL2_K; k++) B[k] = plane_word<INVERT>(row, lane + 32 * k, w, wpr);
+    for (int k = 0; k < K; k++) B[k] = plane_word<INVERT>(row, lane + 32 * k, w, wpr);
 }
 
-__device__ __forceinline__ void row_starts_ends(const uint32_t (&B)[CCL2_K], int lane, uint32_t (&S)[CCL2_K],
-                                                uint32_t (&E)[CCL2_K]) {
+template <int K>
+__device__ __forceinline__ void row_starts_ends(const uint32_t (&B)[K], int lane, uint32_t (&S)[K], uint32_t (&E)[K]) {
 #pragma unroll
-    for (int k = 0; k < CCL2_K; k++) {
+    for (int k = 0; k < K; k++) {
         uint32_t up = __shfl_up_sync(0xffffffffu, B[k], 1), dn = __shfl_down_sync(0xffffffffu, B[k], 1);
         uint32_t cp = k > 0 ? __shfl_sync(0xffffffffu, B[k > 0 ? k - 1 : 0], 31) : 0u;
-        uint32_t cn = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, B[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
+        uint32_t cn = k < K - 1 ? __shfl_sync(0xffffffffu, B[k < K - 1 ? k + 1 : k], 0) : 0u;
         uint32_t Bp = lane ? up : cp, Bn = lane < 31 ? dn : cn;
         S[k] = B[k] & ~((B[k] << 1) | (Bp >> 31));
         E[k] = B[k] & ~((B[k] >> 1) | (Bn << 31));
     }
 }
 
-__device__ __forceinline__ int row_count(const uint32_t (&S)[CCL2_K]) {
+// append the runs of one row to a run table; returns false if the table is full
+template <int K>
+__device__ __forceinline__ bool row_append(const uint32_t (&S)[K], const uint32_t (&E)[K], int lane, int yr, int id0,
+                                           const RunTable &t, int *cursor) {
     int c = 0;
 #pragma unroll
-    for (int k = 0; k < CCL2_K; k++) c += __popc(S[k]);
-    return __reduce_add_sync(0xffffffffu, c);
-}
-
-// write the runs of one row into the shared run table starting at slot `off`
-__device__ __forceinline__ void row_extract(const uint32_t (&S)[CCL2_K], const uint32_t (&E)[CCL2_K], int lane, int off,
-                                            const Ccl2Smem &sm) {
+    for (int k = 0; k < K; k++) c += __popc(S[k]);
+    const int n = __reduce_add_sync(0xffffffffu, c);
+    int off = 0;
+    if (lane == 0) {
+        off = n ? atomicAdd(cursor, n) : 0;
+        t.row[yr] = make_int2(off, n);
+    }
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (n == 0) return true;
+    if (off + n > CCL2_CAP) return false;
     int base = off, ebase = off;       // a run may start in one 1024-px group and end in the next
 #pragma unroll
-    for (int k = 0; k < CCL2_K; k++) {
+    for (int k = 0; k < K; k++) {
         uint32_t s = S[k], e = E[k];
         if (!__any_sync(0xffffffffu, (s | e) != 0)) continue;
         int cs = __popc(s), ce = __popc(e), ps = cs, pe = ce;
@@ -410,19 +416,20 @@ __device__ __forceinline__ void row_extract(const uint32_t (&S)[CCL2_K], const u
         while (s) {
             int bit = __ffs(s) - 1;
             s &= s - 1;
-            sm.xs[is] = (uint16_t)(x0 + bit);
-            sm.parent[1 + is] = 1 + is;
+            t.xs[is] = (uint16_t)(x0 + bit);
+            t.parent[id0 + is] = id0 + is;
             is++;
         }
         while (e) {
             int bit = __ffs(e) - 1;
             e &= e - 1;
-            sm.xe[ie] = (uint16_t)(x0 + bit);
+            t.xe[ie] = (uint16_t)(x0 + bit);
             ie++;
         }
         base += __shfl_sync(0xffffffffu, ps, 31);
         ebase += __shfl_sync(0xffffffffu, pe, 31);
     }
+    return true;
 }
 
 __device__ __forceinline__ int suf_find(int *parent, int x) {
@@ -448,49 +455,29 @@ __device__ __forceinline__ void suf_union(int *parent, int a, int b) {
     }
 }
 
+// id0: id of slot 0 (1 for the background table whose id 0 is the outside, 0 for the foreground table)
 template <bool CONN8, bool OUTSIDE>
-__device__ __forceinline__ void srow_union(const Ccl2Smem &sm, const int *rowoff, int yr, int y, int w, int h, int lane) {
-    const int o0 = rowoff[yr], n = rowoff[yr + 1] - o0;
-    if (n == 0) return;
-    const int p0 = yr > 0 ? rowoff[yr - 1] : 0, np = yr > 0 ? o0 - p0 : 0;
+__device__ __forceinline__ void srow_union(const RunTable &t, int id0, int yr, int y, int w, int h, int lane) {
+    const int2 cur = t.row[yr];
+    if (cur.y == 0) return;
+    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
     const int d = CONN8 ? 1 : 0;
-    for (int i = lane; i < n; i += 32) {
-        const int xs = sm.xs[o0 + i], xe = sm.xe[o0 + i], id = 1 + o0 + i;
-        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(sm.parent, id, 0);
-        if (np) {
-            int lo = 0, hi = np;
+    for (int i = lane; i < cur.y; i += 32) {
+        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
+        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(t.parent, id, 0);
+        if (prv.y) {
+            int lo = 0, hi = prv.y;
             while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if ((int)sm.xe[p0 + mid] < xs - d) lo = mid + 1; else hi = mid;
+                if ((int)t.xe[prv.x + mid] < xs - d) lo = mid + 1; else hi = mid;
             }
-            for (int q = lo; q < np && (int)sm.xs[p0 + q] <= xe + d; q++) suf_union(sm.parent, id, 1 + p0 + q);
+            for (int q = lo; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) suf_union(t.parent, id, id0 + prv.x + q);
         }
     }
 }
 
-// block-wide exclusive scan of cnt[0..n) in place (cnt[n] = total); n <= a few thousand
-__device__ __forceinline__ void block_scan(int *cnt, int n, int *carry_smem) {
-    // warp 0 walks the array 32 entries at a time
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int run = 0;
-        for (int b = 0; b <= n; b += 32) {
-            int i = b + lane;
-            int v = i < n ? cnt[i] : 0, inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (i <= n) cnt[i] = run + inc - v;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) *carry_smem = run;
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
+template <int K>
+__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
     const int lf = blockIdx.x, f = a.f0 + lf;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -502,67 +489,57 @@ __global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, i
         yhi = min(ymax + 1, a.h - 1);
     }
     const int nrows = yhi - ylo + 1;
-    Ccl2Smem sm;
-    sm.rowoff = reinterpret_cast<int *>(csm);
-    sm.rowoff2 = sm.rowoff + (a.h + 2);
-    sm.parent = sm.rowoff2 + (a.h + 2);
-    sm.xs = reinterpret_cast<uint16_t *>(sm.parent + CCL2_CAP + 2);
-    sm.xe = sm.xs + CCL2_CAP;
-    __shared__ int total;
+    RunTable bg, fg;
+    bg.row = reinterpret_cast<int2 *>(csm);
+    fg.row = bg.row + a.h;
+    bg.parent = reinterpret_cast<int *>(fg.row + a.h);
+    fg.parent = bg.parent + CCL2_CAP + 2;
+    bg.xs = reinterpret_cast<uint16_t *>(fg.parent + CCL2_CAP + 2);
+    bg.xe = bg.xs + CCL2_CAP;
+    fg.xs = bg.xe + CCL2_CAP;
+    fg.xe = fg.xs + CCL2_CAP;
+    uint32_t *q4s = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP) + warp * (2 * 32 * K);
+    uint32_t *q3s = q4s + 32 * K;
+    __shared__ int cur_bg, cur_fg, overflow;
+    if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
+    __syncthreads();
     const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr;
     uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr;
 
-    // ---- pass 1 (background, 4-connected): count, scan, extract, union ----
+    // ---- pass 1: background runs (4-connected, linked to the outside) ----
     for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {          // two rows in flight per warp
-        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
+        uint32_t B0[K], B1[K], S[K], E[K];
         const int yr1 = yr + CCL2_WARPS;
-        row_words<true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
-        if (yr1 < nrows) row_words<true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
-        row_starts_ends(B0, lane, S, E);
-        int c = row_count(S);
-        if (lane == 0) sm.rowoff[yr] = c;
+        row_words<K, true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
+        if (yr1 < nrows) row_words<K, true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
+        row_starts_ends<K>(B0, lane, S, E);
+        if (!row_append<K>(S, E, lane, yr, 1, bg, &cur_bg)) overflow = 1;
         if (yr1 < nrows) {
-            row_starts_ends(B1, lane, S, E);
-            c = row_count(S);
-            if (lane == 0) sm.rowoff[yr1] = c;
+            row_starts_ends<K>(B1, lane, S, E);
+            if (!row_append<K>(S, E, lane, yr1, 1, bg, &cur_bg)) overflow = 1;
         }
     }
     __syncthreads();
-    block_scan(sm.rowoff, nrows, &total);
-    if (total > CCL2_CAP) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    if (threadIdx.x == 0) { heavy[f] = 0; sm.parent[0] = 0; }
-    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {
-        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
-        const int yr1 = yr + CCL2_WARPS;
-        row_words<true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
-        if (yr1 < nrows) row_words<true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
-        row_starts_ends(B0, lane, S, E);
-        row_extract(S, E, lane, sm.rowoff[yr], sm);
-        if (yr1 < nrows) {
-            row_starts_ends(B1, lane, S, E);
-            row_extract(S, E, lane, sm.rowoff[yr1], sm);
-        }
-    }
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(bg, 1, yr, ylo + yr, a.w, a.h, lane);
     __syncthreads();
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(sm, sm.rowoff, yr, ylo + yr, a.w, a.h, lane);
-    __syncthreads();
-    // ---- holes -> filled plane; count the foreground runs of the filled rows ----
+    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
     for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
-        uint32_t F[CCL2_K], S[CCL2_K], E[CCL2_K];
-        row_words<false>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, F);
-        const int o0 = sm.rowoff[yr], n = sm.rowoff[yr + 1] - o0;
-        for (int b = 0; b < n; b += 32) {
+        uint32_t F[K], S[K], E[K];
+        row_words<K, false>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, F);
+        const int2 r = bg.row[yr];
+        for (int b = 0; b < r.y; b += 32) {
             const int i = b + lane;
             bool hole = false;
             int xs = 0, xe = 0;
-            if (i < n) { hole = suf_find(sm.parent, 1 + o0 + i) != 0; xs = sm.xs[o0 + i]; xe = sm.xe[o0 + i]; }
+            if (i < r.y) { hole = suf_find(bg.parent, 1 + r.x + i) != 0; xs = bg.xs[r.x + i]; xe = bg.xe[r.x + i]; }
             uint32_t hm = __ballot_sync(0xffffffffu, hole);
             while (hm) {
                 const int src = __ffs(hm) - 1;
                 hm &= hm - 1;
                 const int hxs = __shfl_sync(0xffffffffu, xs, src), hxe = __shfl_sync(0xffffffffu, xe, src);
 #pragma unroll
-                for (int k = 0; k < CCL2_K; k++) {
+                for (int k = 0; k < K; k++) {
                     const int x0 = 32 * (lane + 32 * k);
                     int lo = max(hxs - x0, 0), hi = min(hxe - x0, 31);
                     if (lo <= hi) F[k] |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
@@ -570,56 +547,41 @@ __global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, i
             }
         }
 #pragma unroll
-        for (int k = 0; k < CCL2_K; k++)
+        for (int k = 0; k < K; k++)
             if (lane + 32 * k < a.wpr) fil[(size_t)(ylo + yr) * a.wpr + lane + 32 * k] = F[k];
-        row_starts_ends(F, lane, S, E);
-        const int c = row_count(S);
-        if (lane == 0) sm.rowoff2[yr] = c;
+        row_starts_ends<K>(F, lane, S, E);
+        if (!row_append<K>(S, E, lane, yr, 0, fg, &cur_fg)) overflow = 1;
     }
     __syncthreads();
-    block_scan(sm.rowoff2, nrows, &total);
-    if (total > CCL2_CAP) { if (threadIdx.x == 0) heavy[f] = 1; return; }     // (cannot exceed pass 1 by much; be safe)
-    // ---- pass 2 (filled foreground, 8-connected) ----
-    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {
-        uint32_t B0[CCL2_K], B1[CCL2_K], S[CCL2_K], E[CCL2_K];
-        const int yr1 = yr + CCL2_WARPS;
-        row_words<false>(fil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
-        if (yr1 < nrows) row_words<false>(fil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
-        row_starts_ends(B0, lane, S, E);
-        row_extract(S, E, lane, sm.rowoff2[yr], sm);
-        if (yr1 < nrows) {
-            row_starts_ends(B1, lane, S, E);
-            row_extract(S, E, lane, sm.rowoff2[yr1], sm);
-        }
-    }
-    __syncthreads();
-    // per-root accumulators live in the global scratch, indexed by the compact run id
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    if (threadIdx.x == 0) heavy[f] = 0;
+    const int total = cur_fg;
+    // per-root accumulators live in the global scratch, indexed by the run slot
     int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
     for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
         area2[i] = 0;
         reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
     }
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(sm, sm.rowoff2, yr, ylo + yr, a.w, a.h, lane);
+    // ---- pass 2: filled foreground, 8-connected ----
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(fg, 0, yr, ylo + yr, a.w, a.h, lane);
     __syncthreads();
     // ---- per-run bit-quad area and bounding box -> root ----
     // The 2x2-window masks of a row pair are computed word-parallel (lanes hold the words of rows y-1 and y),
     // parked in the warp's shared scratch, and each run then sums the windows x in [xs-1, xe] it owns.
-    uint32_t *q4s = reinterpret_cast<uint32_t *>(sm.xe + CCL2_CAP) + warp * (2 * 32 * CCL2_K);
-    uint32_t *q3s = q4s + 32 * CCL2_K;
     for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
         const int y = ylo + yr;
-        const int o0 = sm.rowoff2[yr], n = sm.rowoff2[yr + 1] - o0;
-        if (n == 0) continue;
+        const int2 r = fg.row[yr];
+        if (r.y == 0) continue;
         const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
         if (has_up) {
-            uint32_t L[CCL2_K], U[CCL2_K];
-            row_words<false>(fil + (size_t)y * a.wpr, a.w, a.wpr, lane, L);
-            row_words<false>(fil + (size_t)(y - 1) * a.wpr, a.w, a.wpr, lane, U);
+            uint32_t L[K], U[K];
+            row_words<K, false>(fil + (size_t)y * a.wpr, a.w, a.wpr, lane, L);
+            row_words<K, false>(fil + (size_t)(y - 1) * a.wpr, a.w, a.wpr, lane, U);
 #pragma unroll
-            for (int k = 0; k < CCL2_K; k++) {
+            for (int k = 0; k < K; k++) {
                 uint32_t ln = __shfl_down_sync(0xffffffffu, L[k], 1), un = __shfl_down_sync(0xffffffffu, U[k], 1);
-                uint32_t lc = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, L[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
-                uint32_t uc = k < CCL2_K - 1 ? __shfl_sync(0xffffffffu, U[k < CCL2_K - 1 ? k + 1 : k], 0) : 0u;
+                uint32_t lc = k < K - 1 ? __shfl_sync(0xffffffffu, L[k < K - 1 ? k + 1 : k], 0) : 0u;
+                uint32_t uc = k < K - 1 ? __shfl_sync(0xffffffffu, U[k < K - 1 ? k + 1 : k], 0) : 0u;
                 if (lane == 31) { ln = lc; un = uc; }
                 const uint32_t l0 = L[k], l1 = (L[k] >> 1) | (ln << 31), u0 = U[k], u1 = (U[k] >> 1) | (un << 31);
                 q4s[lane + 32 * k] = l0 & l1 & u0 & u1;
@@ -627,9 +589,9 @@ __global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, i
             }
         }
         __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const int xs = sm.xs[o0 + i], xe = sm.xe[o0 + i];
-            const int root = suf_find(sm.parent, 1 + o0 + i) - 1;
+        for (int i = lane; i < r.y; i += 32) {
+            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
+            const int root = suf_find(fg.parent, r.x + i);
             int q = 0;
             if (has_up) {
                 const int x0 = max(xs - 1, 0), x1 = xe;         // windows owned by this run
@@ -651,7 +613,7 @@ __global__ void __launch_bounds__(CCL2_THREADS, 2) k_ccl_frame_smem(CclArgs a, i
     __syncthreads();
     // ---- roots -> component records ----
     for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
-        if (sm.parent[1 + i] != 1 + i) continue;
+        if (fg.parent[i] != i) continue;
         const int ar = __ldcg(area2 + i);
         const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
         const int slot = atomicAdd(a.ncomp + f, 1);
@@ -779,15 +741,21 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.bbox = sc.bbox; a.errflag = errflag;
         a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
         a.min_area = min_area; a.max_area = max_area;
-        if (wpr <= 32 * CCL2_K && heavy) {
-            size_t smem = (size_t)(2 * (h + 2) + CCL2_CAP + 2) * sizeof(int) + (size_t)2 * CCL2_CAP * sizeof(uint16_t) +
-                          (size_t)CCL2_WARPS * 2 * 32 * CCL2_K * sizeof(uint32_t);
-            static size_t configured = 0;
-            if (smem > configured) {
-                FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
+        if (wpr <= 128 && heavy) {
+            const int K = wpr <= 32 ? 1 : (wpr <= 64 ? 2 : 4);
+            size_t smem = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
+                          (size_t)4 * CCL2_CAP * sizeof(uint16_t) + (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
+            static size_t configured[3] = {0, 0, 0};
+            const int ki = K == 1 ? 0 : (K == 2 ? 1 : 2);
+            if (smem > configured[ki]) {
+                if (K == 1) FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else if (K == 2) FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[ki] = smem;
             }
-            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            if (K == 1) k_ccl_frame_smem<1><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            else if (K == 2) k_ccl_frame_smem<2><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            else k_ccl_frame_smem<4><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
