@@ -119,6 +119,20 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(args, info, dom):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/r1k_fused_ncu_full.json); null if the
+    workload differs from the captured one."""
+    try:
+        if dom != "front_end" or (W, H, args.streams, args.frames, args.mode) != (1920, 1080, 8, 16, "full") or \
+                info["gaussian"] > 5:
+            return None
+        with open(os.path.join(ROOT, "profiles", "r1k_fused_ncu_full.json")) as f:
+            return int(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def cpu_baseline(kw, cores, target_s=2.5):
     """Reference CPU path on a bounded sample: one stream per process over all host cores."""
     from oracle import cv2_chain
@@ -314,7 +328,7 @@ def run_b200(args):
     achieved = bytes_launch / (per_call[dom] / 1e3) / 1e9
     step_ms = ms / args.steps
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": dom,
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args, info, dom), "kernel": dom,
                 "kernel_ms_per_launch": round(per_call[dom], 4), "peak_source": peak_src,
                 "alg_bytes_per_frame": round(balg), "alg_formula": "3*W*H + (16/T)*w*h + m*w*h, m=1/8 (bit-packed mask)",
                 "groups_ms_per_step": {k: round(v, 4) for k, v in per_call.items()},
