@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2)
 }
 
 __device__ __forceinline__ double u8_to_f64(uint32_t v) {
-    return __dadd_rn(__hiloint2double(0x43300000, (int)v), -4503599627370496.0);
+    return __int2double_rn((int)v);          // exact for 0..255; one XU op instead of MOV + DADD
 }
 
 template <bool SAFE>
@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
 
 // One thread: 12 gray rows in -> 8 output rows x 4 pixels: blur, mask, threshold bits, background update.
 // INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels.
-template <bool KEEP, bool SAFE, bool INIT, bool MASKED>
+template <bool KEEP, bool SAFE, bool INIT, bool MASKED, bool SH8>
 __device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)[32], uint32_t M, const FusedParams &p,
                                                uint8_t *blur_out, int rows_valid) {
     const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
@@ -130,15 +130,16 @@ __device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)
         win[4][1] = h1;
         if (rr >= 4) {
             const int r = rr - 4;          // output row of this thread
-            uint32_t v[2];
+            uint32_t v[2];      // the two pixels of a pair in bits [0,8) and [16,24) (SH8: in bytes 1 and 3)
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
-                v[j] = (a >> p.shift) & 0x00FF00FFu;
+                v[j] = SH8 ? a : ((a >> p.shift) & 0x00FF00FFu);
             }
             if (KEEP) {
                 if (r < rows_valid) {
-                    uint32_t o = (v[0] & 0xFF) | ((v[0] >> 16) << 8) | ((v[1] & 0xFF) << 16) | ((v[1] >> 16) << 24);
+                    uint32_t o = SH8 ? __byte_perm(v[0], v[1], 0x7531)
+                                     : ((v[0] & 0xFF) | ((v[0] >> 16) << 8) | ((v[1] & 0xFF) << 16) | ((v[1] >> 16) << 24));
                     uint32_t mk = (M >> (4 * r)) & 0xFu;
                     uint32_t keep = ((mk & 1) ? 0u : 0xFFu) | ((mk & 2) ? 0u : 0xFF00u) | ((mk & 4) ? 0u : 0xFF0000u) |
                                     ((mk & 8) ? 0u : 0xFF000000u);
@@ -148,7 +149,8 @@ __device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int idx = 4 * r + c;
-                uint32_t sv = (c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu);
+                uint32_t sv = SH8 ? __byte_perm(v[c >> 1], 0, (c & 1) ? 0x4443 : 0x4441)
+                                  : ((c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu));
                 if (MASKED && (M & (1u << idx))) sv = 0;          // mask_off_areas paints BLACK into blur
                 const double sd = u8_to_f64(sv);
                 if (INIT) bg[idx] = sd;                           // ref_frame = blur.astype(float)
@@ -165,8 +167,8 @@ template <bool KEEP, bool SAFE>
 __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constant__ CUtensorMap tmap, FusedParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     unsigned char *raw = fsm;                                                  // [2][RAW_STAGE] staged BGR rows (TMA)
-    uint32_t *sg = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);        // [FG_ROWS][FG_WORDS] gray
-    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + 2 * RAW_STAGE + FG_ROWS * FG_WORDS * 4);
+    uint32_t *sg2 = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);       // [2][FG_ROWS][FG_WORDS] gray, double buffered
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + 2 * RAW_STAGE + 2 * FG_ROWS * FG_WORDS * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.y;
     const int tile = blockIdx.x;
@@ -217,7 +219,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords;
 
     for (int t = 0; t < p.T; t++) {
-        __syncthreads();            // everyone is done with gray(t-1) and with raw stage (t+1)&1
+        // No barrier here: gray is double buffered, and every thread that gets this far has passed the barrier
+        // of frame t-1, i.e. all conversions out of raw stage (t+1)&1 (frame t-1) are complete.
+        uint32_t *sg = sg2 + (t & 1) * (FG_ROWS * FG_WORDS);
         if (tid == 0 && t + 1 < p.T) {
             mbar_expect_tx(&bars[(t + 1) & 1], RAW_BYTES);
             tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, t + 1, s);
@@ -271,9 +275,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
         uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.T + t) * h + py) * w + px : nullptr;
         const bool okx = px < w;
         uint32_t bits;
-        if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        else if (M) bits = fused_rows<KEEP, SAFE, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        else bits = fused_rows<KEEP, SAFE, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        else if (M) bits = fused_rows<KEEP, SAFE, false, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        else if (p.shift == 8) bits = fused_rows<KEEP, SAFE, false, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
+        else bits = fused_rows<KEEP, SAFE, false, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
         // ---- 8 lanes x 8 rows of nibbles -> one 32-pixel word per lane, coalesced store ----
         uint32_t word = nibble_transpose8(bits, lane);
         {
@@ -326,7 +331,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-#define FUSED_SMEM (2 * RAW_STAGE + FG_ROWS * FG_WORDS * 4 + 16)
+#define FUSED_SMEM (2 * RAW_STAGE + 2 * FG_ROWS * FG_WORDS * 4 + 16)
 
 int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
     if ((((uintptr_t)frames) & 15) || (sstride & 15) || (fstride & 15)) {
