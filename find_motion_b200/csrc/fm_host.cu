@@ -127,7 +127,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
     cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
-    cudaFree(c->any); cudaFree(c->heavy); cudaFree(c->ncomp); cudaFree(c->ncounted); cudaFree(c->comps); cudaFree(c->stats);
+    cudaFree(c->any); cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->ncounted); cudaFree(c->comps); cudaFree(c->stats);
     cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->stage_dev);
     fm_ccl_free(&c->ccl);
     if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
@@ -282,6 +282,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->any, F * 2 * sizeof(int));      // per frame: row range of the dilated mask
     ALLOC(c->ncomp, F * sizeof(int));
     ALLOC(c->heavy, F * sizeof(int));
+    ALLOC(c->rawrange, F * 2 * sizeof(int));
     ALLOC(c->ncounted, F * sizeof(int));
     ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
     ALLOC(c->stats, F * sizeof(fm_frame_stats));
@@ -370,6 +371,7 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
     const bool fused = c->fused;
+    FM_CUDA(cudaMemsetAsync(c->rawrange, 0xFF, (size_t)c->S * n_frames * 2 * sizeof(int), st));
     cudaEvent_t *ev = nullptr;
     if (c->timing) {
         if (c->ev_pending == FM_TIMING_RING && (rc = timing_drain(c))) return rc;

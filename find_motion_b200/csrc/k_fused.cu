@@ -65,6 +65,7 @@ struct FusedParams {
     int threshold;
     double alpha, beta;
     uint8_t *gray_out, *blur_out;   // [S][T][h][w], only with KEEP
+    int *rawrange;                  // [S][T][2] (max y, max h-1-y) of rows with pixels above threshold
 };
 
 __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
@@ -286,6 +287,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
             int xw = (x0 >> 5) + (lane >> 3);
             if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
         }
+        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 8 rows hold something
+            int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
+            atomicMax(rr, min(py + 7, h - 1));
+            atomicMax(rr + 1, h - 1 - py);
+        }
         tw += p.flatwords;
     }
 #pragma unroll
@@ -367,6 +373,7 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
     p.threshold = c->cfg.threshold;
     p.alpha = c->cfg.avg; p.beta = 1.0 - p.alpha;
     p.gray_out = c->gray; p.blur_out = c->blur;
+    p.rawrange = c->rawrange;
     const bool keep = (c->cfg.flags & FM_FLAG_KEEP_PLANES) != 0;
     const bool safe = p.alpha >= 0.0 && p.alpha <= 1.0 && p.threshold >= 0;
     dim3 grid(p.tilesX * p.tilesY, c->S);

@@ -42,13 +42,16 @@ __device__ __forceinline__ uint32_t flat_row_word(const uint32_t *flat, int y, i
 template <bool ALIGNED>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t *__restrict__ tflat,
                                                                  uint32_t *__restrict__ dil, int *__restrict__ rowrange,
-                                                                 const int *__restrict__ rawany, int F, int w, int h,
+                                                                 const int *__restrict__ rawrange, int F, int w, int h,
                                                                  int wpr, int flatwords) {
     int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (warp >= F * h) return;
     int f = warp / h, y = warp - f * h;
-    if (rawany && !rawany[f]) return;          // nothing above threshold in this frame: plane is all zero
+    if (rawrange) {      // rows further than 2 from any pixel above threshold stay untouched (nobody reads them)
+        int rmax = rawrange[2 * f], rmin = h - 1 - rawrange[2 * f + 1];
+        if (rmax < 0 || y < rmin - 3 || y > rmax + 3) return;   // +-2 for the dilation, +-1 for the zero rows the labelling reads
+    }
     const uint32_t *flat = tflat + (size_t)f * flatwords;
     uint32_t *out = dil + ((size_t)f * h + y) * wpr;
     uint32_t anyw = 0;
@@ -671,11 +674,14 @@ __global__ void k_decide(StreamState *__restrict__ state, const int *__restrict_
 // ---------------------------------------------------------------------------------------------
 // exports for the parity tests
 // ---------------------------------------------------------------------------------------------
+// rowrange (optional): rows outside [h-1-rowrange[1], rowrange[0]] were never written and read as zero
 __global__ void k_bits_to_u8(const uint32_t *__restrict__ plane, uint8_t *__restrict__ dst, int w, int h, int wpr,
-                             uint8_t on) {
+                             uint8_t on, const int *__restrict__ rowrange) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    dst[(size_t)y * w + x] = ((plane[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? on : 0;
+    bool live = true;
+    if (rowrange) live = rowrange[0] >= 0 && y <= rowrange[0] && y >= h - 1 - rowrange[1];
+    dst[(size_t)y * w + x] = (live && ((plane[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u)) ? on : 0;
 }
 
 __global__ void k_u8_to_bits(const uint8_t *__restrict__ src, uint32_t *__restrict__ plane, int w, int h, int wpr) {
@@ -692,7 +698,7 @@ __global__ void k_u8_to_bits(const uint8_t *__restrict__ src, uint32_t *__restri
 int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st) {
     const uint32_t *pl = c->dil + ((size_t)stream * c->last_T + t) * c->h * c->wpr;
     dim3 grid((c->w + 127) / 128, c->h);
-    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 255);
+    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 255, c->any + 2 * ((size_t)stream * c->last_T + t));
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -700,7 +706,7 @@ int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cuda
 int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st) {
     const uint32_t *pl = c->maskbits + (size_t)stream * c->h * c->wpr;
     dim3 grid((c->w + 127) / 128, c->h);
-    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 1);
+    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 1, nullptr);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -774,10 +780,10 @@ int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats
     FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
     int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (c->w % 32 == 0)
-        k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, nullptr, F, c->w, c->h,
+        k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
                                                                c->wpr, c->ntiles * FM_TILE_WORDS);
     else
-        k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, nullptr, F, c->w, c->h,
+        k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
                                                                 c->wpr, c->ntiles * FM_TILE_WORDS);
     FM_LAUNCH_CHECK();
     int rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,

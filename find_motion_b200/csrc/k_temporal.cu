@@ -32,7 +32,7 @@ __device__ __forceinline__ double fm_bg_update(double bg, uint32_t src, double a
 __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ blur, double *__restrict__ bg,
                                                   uint32_t *__restrict__ tflat, const StreamState *__restrict__ state,
                                                   int T, int N, int ntiles, int threshold, double alpha,
-                                                  double beta) {
+                                                  double beta, int *__restrict__ rawrange, int w, int h) {
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -81,6 +81,12 @@ __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ bl
         uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 1);
         if ((lane & 1) == 0) *tw = bits | (hi << 16);
         tw += (size_t)ntiles * FM_TILE_WORDS;
+        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // rows touched by this 512-pixel tile
+            int ya = (tile * FM_TILE_PX) / w, yb = min((tile * FM_TILE_PX + FM_TILE_PX - 1) / w, h - 1);
+            int *rr = rawrange + 2 * ((size_t)s * T + t);
+            atomicMax(rr, yb);
+            atomicMax(rr + 1, h - 1 - ya);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) bgt[j * 32 + lane] = make_double2(b[2 * j], b[2 * j + 1]);
@@ -100,7 +106,7 @@ int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st) {
     double beta = 1.0 - alpha;
     dim3 grid((c->ntiles + 7) / 8, c->S);
     k_temporal<<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
-                                     alpha, beta);
+                                     alpha, beta, c->rawrange, c->w, c->h);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
