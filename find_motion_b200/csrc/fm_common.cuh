@@ -82,6 +82,8 @@ struct fm_ctx {
     size_t stage_bytes;
     fm_frame_stats *stats_pinned;
     cudaStream_t own_stream;
+    cudaStream_t side_stream;  // contour stage of the first half of a call overlaps the second half's K1
+    cudaEvent_t ev_half[3];
     // timing
     bool timing;               // bracket the kernel groups with events (no sync inside fm_process)
     cudaEvent_t *evs;          // [FM_TIMING_RING][4]
@@ -119,7 +121,10 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                        cudaStream_t st);
 int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st);
 int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
-                    cudaStream_t st);
+                    cudaStream_t st, int t0, int Th, int force_bg);
+int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st);
+int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st);
+int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_masks(fm_ctx *c, int stream, int n_polys, const int *offs, const int *pts_scaled,
                     int npts, cudaStream_t st);

@@ -132,6 +132,9 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     fm_ccl_free(&c->ccl);
     if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    for (int i = 0; i < 3; i++)
+        if (c->ev_half[i]) cudaEventDestroy(c->ev_half[i]);
     if (c->evs) {
         for (int i = 0; i < 4 * FM_TIMING_RING; i++) cudaEventDestroy(c->evs[i]);
         delete[] c->evs;
@@ -302,6 +305,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     int nb = (int)std::min<size_t>(F, std::max<size_t>(1, budget / per_frame));
     if ((rc = fm_ccl_alloc(&c->ccl, nb, c->h, cap))) return fail(rc);
     FM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) FM_CUDA(cudaEventCreateWithFlags(&c->ev_half[i], cudaEventDisableTiming));
     *out = c;
     return FM_OK;
 }
@@ -378,8 +383,30 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
         ev = c->evs + 4 * c->ev_pending++;
         FM_CUDA(cudaEventRecord(ev[0], st));
     }
-    if (fused) {
-        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
+    if (fused && n_frames >= 4 && (c->cfg.flags & FM_FLAG_OVERLAP)) {
+        // two halves: the dilation + contour kernels of the first half run on a side stream while K1 works
+        // on the second half; the caller's stream joins before the call returns its work to the caller
+        const int Ta = n_frames / 2, Tb = n_frames - Ta;
+        cudaStream_t sd = c->side_stream;
+        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, 0, Ta, 0))) return rc;
+        FM_CUDA(cudaEventRecord(c->ev_half[0], st));
+        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, Ta, Tb, 1))) return rc;
+        FM_CUDA(cudaEventRecord(c->ev_half[1], st));
+        if (ev) { FM_CUDA(cudaEventRecord(ev[1], st)); FM_CUDA(cudaEventRecord(ev[2], st)); }
+        FM_CUDA(cudaStreamWaitEvent(sd, c->ev_half[0], 0));
+        if ((rc = fm_launch_morph_begin(c, n_frames, sd))) return rc;
+        if ((rc = fm_launch_morph_range(c, n_frames, 0, Ta, sd))) return rc;
+        FM_CUDA(cudaStreamWaitEvent(sd, c->ev_half[1], 0));
+        if ((rc = fm_launch_morph_range(c, n_frames, Ta, Tb, sd))) return rc;
+        if ((rc = fm_launch_decide(c, n_frames, sd, stats_dev))) return rc;
+        FM_CUDA(cudaEventRecord(c->ev_half[2], sd));
+        FM_CUDA(cudaStreamWaitEvent(st, c->ev_half[2], 0));
+        if (ev) FM_CUDA(cudaEventRecord(ev[3], st));
+        c->last_T = n_frames;
+        c->planes_valid = true;
+        return FM_OK;
+    } else if (fused) {
+        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, 0, n_frames, 0))) return rc;
         if (ev) { FM_CUDA(cudaEventRecord(ev[1], st)); FM_CUDA(cudaEventRecord(ev[2], st)); }
     } else {
         if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;

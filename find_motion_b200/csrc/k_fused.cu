@@ -54,7 +54,9 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
 }
 
 struct FusedParams {
-    int T, w, h, wpr;
+    int T, w, h, wpr;           // T = frames processed by this launch
+    int t0, Ttot;               // they are frames t0 .. t0+T-1 of a Ttot-frame call (per-stream arrays have stride Ttot)
+    int force_bg;               // the background is valid whatever the stream state says (second half of a call)
     int tilesX, tilesY;
     double *bg;                 // [S][tiles][8 warps][8 rows][2 pairs][32 lanes] double2
     const uint32_t *maskbits;   // [S][h][wpr]
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     const int x0 = tx * FT_W, y0 = ty * FT_H;
     const int w = p.w, h = p.h;
     const bool border = (x0 == 0) || (x0 + FT_W >= w) || (y0 == 0) || (y0 + FT_H >= h);
-    const bool has_bg = p.state[s].has_bg != 0;
+    const bool has_bg = p.force_bg || p.state[s].has_bg != 0;
 
     // this thread's pixels: columns x0 + 4*lane .. +3, rows y0 + 8*warp .. +7
     const int px = x0 + 4 * lane, py = y0 + 8 * warp;
@@ -215,9 +217,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bars[0], RAW_BYTES);
-        tma_load_4d(raw, &tmap, &bars[0], cx, cy, 0, s);
+        tma_load_4d(raw, &tmap, &bars[0], cx, cy, p.t0, s);
     }
-    uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords;
+    uint32_t *tw = p.tbits + ((size_t)s * p.Ttot + p.t0) * p.flatwords;
 
     for (int t = 0; t < p.T; t++) {
         // No barrier here: gray is double buffered, and every thread that gets this far has passed the barrier
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
         uint32_t *sg = sg2 + (t & 1) * (FG_ROWS * FG_WORDS);
         if (tid == 0 && t + 1 < p.T) {
             mbar_expect_tx(&bars[(t + 1) & 1], RAW_BYTES);
-            tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, t + 1, s);
+            tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, p.t0 + t + 1, s);
         }
         mbar_wait(&bars[t & 1], (t >> 1) & 1);
         // ---- staged BGR -> gray bytes in shared memory (tile + halo), 4 pixels per unit ----
@@ -267,13 +269,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
                 int ry = u / (FT_W / 4), ux = u - ry * (FT_W / 4);
                 int gy = y0 + ry, gx = x0 + 4 * ux;
                 if (gy < h && gx < w)
-                    *reinterpret_cast<uint32_t *>(p.gray_out + (((size_t)s * p.T + t) * h + gy) * w + gx) =
+                    *reinterpret_cast<uint32_t *>(p.gray_out + (((size_t)s * p.Ttot + p.t0 + t) * h + gy) * w + gx) =
                         sg[(ry + 2) * FG_WORDS + ux + 1];
             }
         }
         // ---- separable blur on packed pairs, sliding 5-row window, then the temporal update ----
         const uint32_t *sgw = sg + (8 * warp) * FG_WORDS + lane;
-        uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.T + t) * h + py) * w + px : nullptr;
+        uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.Ttot + p.t0 + t) * h + py) * w + px : nullptr;
         const bool okx = px < w;
         uint32_t bits;
         if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
             if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
         }
         if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 8 rows hold something
-            int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
+            int *rr = p.rawrange + 2 * ((size_t)s * p.Ttot + p.t0 + t);
             atomicMax(rr, min(py + 7, h - 1));
             atomicMax(rr + 1, h - 1 - py);
         }
@@ -339,7 +341,8 @@ static PFN_encodeTiled get_encode() {
 
 #define FUSED_SMEM (2 * RAW_STAGE + 2 * FG_ROWS * FG_WORDS * 4 + 16)
 
-int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
+int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st, int t0,
+                    int Th, int force_bg) {
     if ((((uintptr_t)frames) & 15) || (sstride & 15) || (fstride & 15)) {
         fm_set_error("fused front end needs 16-byte aligned frames and strides (TMA)");
         return FM_EINVAL;
@@ -357,7 +360,8 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fm_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FM_ECUDA; }
     FusedParams p;
-    p.T = T; p.w = c->w; p.h = c->h; p.wpr = c->wpr;
+    p.T = Th; p.t0 = t0; p.Ttot = T; p.force_bg = force_bg;
+    p.w = c->w; p.h = c->h; p.wpr = c->wpr;
     p.tilesX = (c->w + FT_W - 1) / FT_W; p.tilesY = (c->h + FT_H - 1) / FT_H;
     p.bg = c->bg; p.maskbits = c->maskbits; p.tbits = c->tflat;
     p.flatwords = (size_t)c->ntiles * FM_TILE_WORDS;

@@ -43,11 +43,13 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t *__restrict__ tflat,
                                                                  uint32_t *__restrict__ dil, int *__restrict__ rowrange,
                                                                  const int *__restrict__ rawrange, int F, int w, int h,
-                                                                 int wpr, int flatwords) {
+                                                                 int wpr, int flatwords, int T, int t0, int Th) {
+    // F = S*Th local frames: local frame lf is frame t0 + lf % Th of stream lf / Th, stored at s*T + t
     int warp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (warp >= F * h) return;
-    int f = warp / h, y = warp - f * h;
+    int lf = warp / h, y = warp - lf * h;
+    int f = (lf / Th) * T + t0 + lf % Th;
     if (rawrange) {      // rows further than 2 from any pixel above threshold stay untouched (nobody reads them)
         int rmax = rawrange[2 * f], rmin = h - 1 - rawrange[2 * f + 1];
         if (rmax < 0 || y < rmin - 3 || y > rmax + 3) return;   // +-2 for the dilation, +-1 for the zero rows the labelling reads
@@ -93,7 +95,8 @@ struct CclArgs {
     const uint32_t *plane;     // [F][h][wpr] dilated bit plane
     uint32_t *fill;            // [F][h][wpr] dilated plane with holes filled (written by the kernel)
     const int *rowrange;       // [F][2] from k_dilate (NULL: label every row of every frame)
-    int f0, nf;                // frames [f0, f0+nf) of the call are in this sub-batch
+    int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
+    int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
     int w, h, wpr, cap;
     size_t slots;
     uint16_t *xs, *xe;
@@ -321,7 +324,7 @@ __device__ __forceinline__ void collect_row(const CclArgs &a, int lf, int f, int
 // pixels are visited; quiet frames exit at once.
 #define CCL_THREADS 1024
 __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const int *__restrict__ heavy) {
-    const int lf = blockIdx.x, f = a.f0 + lf;
+    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
     if (heavy && !heavy[f]) return;                 // already labelled by k_ccl_frame_smem
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
     int ylo = 0, yhi = a.h - 1;
@@ -482,7 +485,7 @@ __device__ __forceinline__ void srow_union(const RunTable &t, int id0, int yr, i
 template <int K>
 __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
-    const int lf = blockIdx.x, f = a.f0 + lf;
+    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ylo = 0, yhi = a.h - 1;
     if (a.rowrange) {
@@ -737,11 +740,12 @@ void fm_ccl_free(CclScratch *s) {
 // labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
 static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
-                   int max_area, int *errflag, int *heavy, cudaStream_t st) {
+                   int max_area, int *errflag, int *heavy, int T, int t0, int Th, cudaStream_t st) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
         CclArgs a;
         a.plane = plane; a.fill = fill; a.rowrange = rowrange;
+        a.T = T; a.t0 = t0; a.Th = Th;
         a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
         a.bbox = sc.bbox; a.errflag = errflag;
@@ -773,26 +777,42 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
     return FM_OK;
 }
 
-int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
+// clears the per-frame result slots of a call (row ranges, counts); once per call, before any range
+int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st) {
     const int F = c->S * T;
     FM_CUDA(cudaMemsetAsync(c->any, 0xFF, (size_t)F * 2 * sizeof(int), st));     // row ranges: (-1, -1)
     FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (size_t)F * sizeof(int), st));
     FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
+    return FM_OK;
+}
+
+// dilation + contours of frames [t0, t0+Th) of every stream of a T-frame call
+int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st) {
+    const int F = c->S * Th;
     int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (c->w % 32 == 0)
         k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                               c->wpr, c->ntiles * FM_TILE_WORDS);
+                                                               c->wpr, c->ntiles * FM_TILE_WORDS, T, t0, Th);
     else
         k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                                c->wpr, c->ntiles * FM_TILE_WORDS);
+                                                                c->wpr, c->ntiles * FM_TILE_WORDS, T, t0, Th);
     FM_LAUNCH_CHECK();
-    int rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                     c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, st);
-    if (rc) return rc;
+    return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
+                   c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st);
+}
+
+int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
     k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(c->state, c->ncomp, c->ncounted, c->stats, stats_out, c->S, T,
                                                  c->info.cache_frames, c->info.min_movement_frames);
     FM_LAUNCH_CHECK();
     return FM_OK;
+}
+
+int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
+    int rc;
+    if ((rc = fm_launch_morph_begin(c, T, st))) return rc;
+    if ((rc = fm_launch_morph_range(c, T, 0, T, st))) return rc;
+    return fm_launch_decide(c, T, st, stats_out);
 }
 
 // standalone labelling of one host plane (parity tests of the contour stage)
@@ -817,7 +837,7 @@ int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n,
     dim3 grid((wpr + 63) / 64, h);
     k_u8_to_bits<<<grid, 64>>>(d8, pl, w, h, wpr);
     FM_LAUNCH_CHECK();
-    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, cnt + 3, 0);
+    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, cnt + 3, 1, 0, 1, 0);
     FM_CUDA(cudaDeviceSynchronize());
     if (rc) return rc;
     int hc[3];

@@ -55,6 +55,9 @@ typedef struct fm_config {
 
 #define FM_FLAG_KEEP_PLANES 1   /* keep gray/blur planes of the last call for fm_debug_planes */
 #define FM_FLAG_NO_FUSED    2   /* force the generic multi-kernel front end (A/B testing) */
+#define FM_FLAG_OVERLAP     4   /* experimental: split a call in two halves and run the contour stage of the
+                                   first on a side stream under K1 of the second (measured slower on B200:
+                                   the labelling CTAs evict K1 CTAs and the background is streamed twice) */
 
 /* Derived parameters, exactly as the reference computes them. */
 typedef struct fm_info {

@@ -87,3 +87,44 @@ def test_run_vid_reports_errors_like_the_reference():
     assert res[0] is None and "Filename required" in res[2]
     res = run_vid("/nonexistent/file.avi", box_size=100)
     assert res[0] is None and res[2] != ""
+
+
+def test_run_vid_on_a_real_video_file(tmp_path):
+    """End to end through cv2.VideoCapture / cv2.VideoWriter: a lossless FFV1 clip in, *_motion.avi out
+    with exactly the frames the reference writes (golden trace of the same clip)."""
+    cv2 = pytest.importorskip("cv2")
+    from find_motion_b200.video_motion import run_vid
+    fx = helpers.load_golden("full_256x192_k5")
+    clip = helpers.golden_clip(fx)
+    W, H = fx["clip"]["W"], fx["clip"]["H"]
+    src = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"FFV1"), fx["kwargs"]["fps"], (W, H))
+    if not wr.isOpened():
+        pytest.skip("FFV1 writer not available in this cv2 build")
+    for f in clip:
+        wr.write(f)
+    wr.release()
+    cap = cv2.VideoCapture(src)
+    ok, first = cap.read()
+    cap.release()
+    if not ok or not (first == clip[0]).all():
+        pytest.skip("FFV1 round trip is not lossless here")
+    outdir = tmp_path / "out"
+    outdir.mkdir()
+    kw = dict(fx["kwargs"], outdir=str(outdir), codec="FFV1", chunk=8)
+    wrote, name, err, seen = run_vid(src, **kw)
+    assert err == "" and wrote is True and name == src and seen == ()
+    outs = sorted(outdir.glob("*_motion.avi"))
+    assert len(outs) == 1
+    cap = cv2.VideoCapture(str(outs[0]))
+    got = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        got.append(f)
+    cap.release()
+    want = expected_written(fx["trace"], fx["params"]["cache_frames"])
+    assert len(got) == len(want) == fx["writes"]
+    for f, t in zip(got, want):
+        assert (f == clip[t]).all()
