@@ -123,6 +123,20 @@ class MotionEngine:
         m = min(n.value, max_n)
         return n.value, [(buf[i].area_x2, (buf[i].x, buf[i].y, buf[i].w, buf[i].h)) for i in range(m)]
 
+    def motion_boxes(self, stream, t):
+        """The rectangles `--show` would draw for frame t (find_motion.py:690-692, 787-813): for every contour
+        that find_movement counts, make_area_from_rect(boundingRect) scaled back to source pixels with
+        scale_area(area, 1 / scale) (int() truncation).  Sorted."""
+        _, comps = self.components(stream, t)
+        inv = 1 / self.info["scale"]
+        out = []
+        for area2, (x, y, w, h) in comps:
+            area = area2 / 2.0
+            if self.info["max_area"] < area < self.info["min_area"]:      # find_motion.py:684
+                continue
+            out.append(((int(x * inv), int(y * inv)), (int((x + w) * inv), int((y + h) * inv))))
+        return sorted(out)
+
     def planes(self, stream, t, gray=True, blur=True, thresh=True, bg=True):
         out = {}
         arrs = {}

@@ -128,3 +128,21 @@ def test_run_vid_on_a_real_video_file(tmp_path):
     assert len(got) == len(want) == fx["writes"]
     for f, t in zip(got, want):
         assert (f == clip[t]).all()
+
+
+def test_motion_boxes_match_the_reference_overlay():
+    """the boxes --show would draw = boundingRect scaled by 1/scale (find_motion.py:787-813)."""
+    import torch
+    from find_motion_b200.engine import MotionEngine
+    fx = helpers.load_golden("cfg2_1080p_D_masks")
+    clip = helpers.golden_clip(fx)[:24]
+    c = fx["clip"]
+    with MotionEngine(c["W"], c["H"], n_streams=1, max_frames=8, **fx["kwargs"]) as eng:
+        dev = torch.from_numpy(clip).cuda()
+        inv = 1 / fx["params"]["scale"]
+        for t0 in range(0, 24, 8):
+            eng.process(dev[None, t0:t0 + 8])
+            for t in range(t0, t0 + 8):
+                want = sorted(((int(x * inv), int(y * inv)), (int((x + w) * inv), int((y + h) * inv)))
+                              for (x, y, w, h) in fx["trace"][t]["boxes"])
+                assert eng.motion_boxes(0, t - t0) == want
