@@ -271,6 +271,17 @@ struct K0GParams {
     const float4 *g4w;       // padded weights
 };
 
+__device__ __noinline__ void copy_partial_block(unsigned char *d, const uint8_t *origin, long o0, long row_lo,
+                                                long row_hi) {
+#pragma unroll 1
+    for (int b = 0; b < 16; b++) {
+        long o = o0 + b;
+        d[b] = (o >= row_lo && o < row_hi) ? origin[o] : 0;
+    }
+}
+
+// PF = 16-byte blocks per lane of one source segment (registers used to prefetch the next row)
+template <int PF>
 __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K0GParams gp, int segpitch, int tasks,
                                                                    int nq, int dxw) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -289,34 +300,54 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
     const bool live = lane < dxw && dx < p.w;
     const int b_lo = gp.g4start[dxa] * 3;
     const int b_hi = min((gp.g4start[dxb - 1] + 4 * gp.g4n[dxb - 1]) * 3, rowbytes);
+    const int nbytes = b_hi - b_lo;
     int gs = 0, gn = 0;
     const float4 *gw = gp.g4w;
     if (live) { gs = gp.g4start[dx]; gn = gp.g4n[dx]; gw += gp.g4off[dx]; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int j = 0; j < ny; j++) {
-        const int sy = p.yidx[y0 + j];
-        const float beta = p.ywt[y0 + j];
-        const uint8_t *seg = src + (size_t)sy * rowbytes + b_lo;
-        const int nbytes = b_hi - b_lo;
+    uint4 *dst16 = reinterpret_cast<uint4 *>(rowbuf);
+    // software pipeline: the 16-byte blocks of row j+1 are loaded into registers while row j is reduced
+    uint4 pre[PF];
+    auto seg_of = [&](int j) { return src + (size_t)p.yidx[y0 + j] * rowbytes + b_lo; };
+    auto issue = [&](int j) {
+        const uint8_t *seg = seg_of(j);
         const int mis = (int)((uintptr_t)seg & 15);
         const uint4 *seg16 = reinterpret_cast<const uint4 *>(seg - mis);
         const int n16 = (mis + nbytes + 15) >> 4;
-        uint4 *dst16 = reinterpret_cast<uint4 *>(rowbuf);
         const long row_lo = -(long)b_lo + mis, row_hi = (long)rowbytes - b_lo + mis;
-        __syncwarp();
-        for (int i = lane; i < n16; i += 32) {
-            long o0 = (long)i * 16;
-            if (o0 >= row_lo && o0 + 16 <= row_hi) {
-                dst16[i] = __ldg(seg16 + i);
-            } else {
-                unsigned char *d = reinterpret_cast<unsigned char *>(dst16 + i);
-                for (int b = 0; b < 16; b++) {
-                    long o = o0 + b;
-                    d[b] = (o >= row_lo && o < row_hi) ? seg[o - mis] : 0;
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            const int i = lane + 32 * k;
+            const long o0 = (long)i * 16;
+            if (i < n16 && o0 >= row_lo && o0 + 16 <= row_hi) pre[k] = __ldg(seg16 + i);
+        }
+    };
+    auto commit = [&](int j) {           // registers (or, for partial blocks at the row ends, bytes) -> shared
+        const uint8_t *seg = seg_of(j);
+        const int mis = (int)((uintptr_t)seg & 15);
+        const int n16 = (mis + nbytes + 15) >> 4;
+        const long row_lo = -(long)b_lo + mis, row_hi = (long)rowbytes - b_lo + mis;
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            const int i = lane + 32 * k;
+            const long o0 = (long)i * 16;
+            if (i < n16) {
+                if (o0 >= row_lo && o0 + 16 <= row_hi) {
+                    dst16[i] = pre[k];
+                } else {
+                    copy_partial_block(reinterpret_cast<unsigned char *>(dst16 + i), seg - mis, o0, row_lo, row_hi);
                 }
             }
         }
+        return mis;
+    };
+    issue(0);
+    for (int j = 0; j < ny; j++) {
+        const float beta = p.ywt[y0 + j];
+        __syncwarp();                      // readers of the previous row are done
+        const int mis = commit(j);
         __syncwarp();
+        if (j + 1 < ny) issue(j + 1);
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(rowbuf + mis - b_lo + 3 * gs);
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll 2
@@ -589,12 +620,19 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
             if (aligned4 && c->g4w) {
                 static size_t configured_g = 0;
                 if (smemw > configured_g) {
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
                     configured_g = smemw;
                 }
                 K0GParams gp;
                 gp.g4start = c->g4start; gp.g4n = c->g4n; gp.g4off = c->g4off; gp.g4w = c->g4w;
-                k_resize_gray_g4<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+                const int blocks16 = segpitch / 16 + 1;         // upper bound of 16-byte blocks per segment
+                const int gridw = (tasks + K0W_WARPS - 1) / K0W_WARPS;
+                if (blocks16 <= 4 * 32) k_resize_gray_g4<4><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+                else if (blocks16 <= 8 * 32) k_resize_gray_g4<8><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+                else if (blocks16 <= 16 * 32) k_resize_gray_g4<16><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+                else k_resize_gray_warp<<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
             } else {
                 k_resize_gray_warp<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
             }
