@@ -31,8 +31,8 @@ METRIC = "1080p frames/sec (whole box)"   # other --size values are characterisa
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="full", choices=["full", "default"],
                     help="full = --box-size 1920 (full-resolution stencil); default = reference default --box-size 100")
@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def stop(self):
         self._halt.set()
@@ -154,14 +154,11 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     from oracle import cv2_chain
     probe = cv2_chain.time_cpu_path(W, H, kw, 1, 4, 1, clip_len=4)
-    frames = max(4, min(400, int(2.0 / (probe["seconds"] / 4))))
-    for _ in range(args.warmup):
-        cv2_chain.time_cpu_path(W, H, kw, cores, max(2, frames // 8), cores, clip_len=4)
-    tot_f, tot_s = 0, 0.0
-    for _ in range(args.steps):
-        r = cv2_chain.time_cpu_path(W, H, kw, cores, frames, cores, clip_len=8)
-        tot_f += r["frames"]
-        tot_s += r["seconds"]
+    per_frame = probe["seconds"] / 4
+    # bounded sample: the whole warm-up + K steps loop of a worker lasts ~45 s at most
+    frames = max(1, min(400, int(45.0 / per_frame / max(1, args.steps + args.warmup))))
+    r = cv2_chain.time_cpu_path(W, H, kw, cores, frames, cores, clip_len=8, steps=args.steps, warmup=args.warmup)
+    tot_f, tot_s = r["frames"], r["seconds"]
     fps = tot_f / tot_s
     info = probe_info(kw)
     line = {
@@ -393,7 +390,7 @@ def secondary_regimes(args, ring_dev, torch, dist):
         try:
             with MotionEngine(W, H, n_streams=S, max_frames=T, **kw) as eng:
                 a = argparse.Namespace(**vars(args))
-                a.steps, a.warmup = max(3, args.steps // 4), 3
+                a.steps, a.warmup = max(3, min(40, args.steps // 4)), 3
                 ms = time_engine(eng, ring_dev, a, torch, dist, 1)
                 fps = S * T * a.steps / (ms / 1e3)
                 balg = alg_bytes_per_frame(eng.w, eng.h, T)

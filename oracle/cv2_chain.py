@@ -108,6 +108,7 @@ def _worker(spec):
     W, H, kw = spec["W"], spec["H"], spec["kw"]
     if kw.get("mask_areas"):
         kw["mask_areas"] = [tuple(tuple(p) for p in a) for a in kw["mask_areas"]]
+    steps, warmup = spec.get("steps", 1), spec.get("warmup", 0)
     out = []
     for seed in spec["seeds"]:
         clip = synth.make_clip(W, H, spec["clip_len"], seed, fps=kw.get("fps", 30))
@@ -118,18 +119,23 @@ def _worker(spec):
         else:
             from oracle import restated as R
             step = R.StreamOracle(W, H, **kw).process
+        moved, i = 0, 0
+        for _ in range(warmup * spec["frames"]):
+            step(clip[i % spec["clip_len"]])
+            i += 1
         t0 = time.perf_counter()
-        moved = 0
-        for i in range(spec["frames"]):
+        for _ in range(steps * spec["frames"]):
             moved += int(step(clip[i % spec["clip_len"]])["movement"])
+            i += 1
         out.append({"seconds": time.perf_counter() - t0, "moved": moved})
     return out
 
 
 def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8, seed0=2000, cv_threads=1,
-                  timeout=600):
-    """Run `n_streams` synthetic streams of `frames_per_stream` frames over `processes` worker
-    processes (streams dealt round-robin).  Returns dict(fps, seconds, frames, processes, engine)."""
+                  timeout=900, steps=1, warmup=0):
+    """Run `n_streams` synthetic streams over `processes` worker processes (streams dealt round-robin);
+    every stream does `warmup` untimed + `steps` timed steps of `frames_per_stream` frames.
+    Returns dict(fps, seconds, frames, processes, engine)."""
     import json
     import os
     import subprocess
@@ -140,7 +146,8 @@ def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8,
     procs = []
     for p in range(processes):
         spec = {"W": W, "H": H, "kw": kw, "seeds": [seed0 + s for s in range(p, n_streams, processes)],
-                "clip_len": clip_len, "frames": frames_per_stream, "cv_threads": cv_threads, "use_cv2": use_cv2}
+                "clip_len": clip_len, "frames": frames_per_stream, "cv_threads": cv_threads, "use_cv2": use_cv2,
+                "steps": steps, "warmup": warmup}
         procs.append(subprocess.Popen([sys.executable, "-m", "oracle.cv2_chain", json.dumps(spec)], cwd=root,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     busy = 0.0
@@ -150,7 +157,7 @@ def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8,
             raise RuntimeError("cpu worker failed: " + se[-500:])
         res = json.loads(so.strip().splitlines()[-1])
         busy = max(busy, sum(r["seconds"] for r in res))     # a worker runs its streams back to back
-    frames = n_streams * frames_per_stream
+    frames = n_streams * frames_per_stream * steps
     return {"fps": frames / busy, "seconds": busy, "frames": frames, "processes": processes,
             "engine": "cv2 call chain" if use_cv2 else "numpy oracle", "cv_threads": cv_threads}
 
