@@ -12,6 +12,7 @@
 #define FM_TILE_PX 512         // pixels per background tile: 32 lanes x 16 px
 #define FM_TILE_WORDS 16       // 32-bit threshold words per tile
 #define FM_TIMING_RING 1024
+#define FM_MAX_DEVICES 64      // per-device caches of kernel attributes (cudaFuncSetAttribute is per device)
 
 struct StreamState {           // per stream, device resident (find_motion.py:362-371)
     int has_bg;                // ref_frame is not None

@@ -610,7 +610,8 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
             int nq = (c->w + 31) / 32, dxw = (c->w + nq - 1) / nq;
             int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 10) + 32 + 15) & ~15;
             size_t smemw = (size_t)K0W_WARPS * segpitch;
-            static size_t configured_w = 0;
+            static size_t configured_w_dev[FM_MAX_DEVICES] = {0};
+            size_t &configured_w = configured_w_dev[c->cfg.device % FM_MAX_DEVICES];
             if (smemw > configured_w) {
                 FM_CUDA(cudaFuncSetAttribute(k_resize_gray_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
                 configured_w = smemw;
@@ -618,7 +619,8 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
             int tasks = c->h * F * nq;
             const bool aligned4 = ((((uintptr_t)frames) | sstride | fstride | ((size_t)c->W * 3)) & 3) == 0;
             if (aligned4 && c->g4w) {
-                static size_t configured_g = 0;
+                static size_t configured_g_dev[FM_MAX_DEVICES] = {0};
+                size_t &configured_g = configured_g_dev[c->cfg.device % FM_MAX_DEVICES];
                 if (smemw > configured_g) {
                     FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
                     FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
@@ -643,7 +645,8 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                 fm_set_error("resize front end needs %zu bytes of shared memory (frame too wide / ratio too large)", smem);
                 return FM_ERANGE;
             }
-            static size_t configured = 0;
+            static size_t configured_dev[FM_MAX_DEVICES] = {0};
+            size_t &configured = configured_dev[c->cfg.device % FM_MAX_DEVICES];
             if (smem > configured) {
                 FM_CUDA(cudaFuncSetAttribute(k_resize_gray, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = smem;

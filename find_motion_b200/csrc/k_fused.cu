@@ -381,7 +381,8 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
     const bool keep = (c->cfg.flags & FM_FLAG_KEEP_PLANES) != 0;
     const bool safe = p.alpha >= 0.0 && p.alpha <= 1.0 && p.threshold >= 0;
     dim3 grid(p.tilesX * p.tilesY, c->S);
-    static bool configured = false;
+    static bool configured_dev[FM_MAX_DEVICES] = {false};
+    bool &configured = configured_dev[c->cfg.device % FM_MAX_DEVICES];
     if (!configured) {
         FM_CUDA(cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
         FM_CUDA(cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));

@@ -755,7 +755,10 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
             const int K = wpr <= 32 ? 1 : (wpr <= 64 ? 2 : 4);
             size_t smem = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
                           (size_t)4 * CCL2_CAP * sizeof(uint16_t) + (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
-            static size_t configured[3] = {0, 0, 0};
+            static size_t configured_dev[FM_MAX_DEVICES][3] = {{0}};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            size_t *configured = configured_dev[dev % FM_MAX_DEVICES];
             const int ki = K == 1 ? 0 : (K == 2 ? 1 : 2);
             if (smem > configured[ki]) {
                 if (K == 1) FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
