@@ -1,8 +1,11 @@
 // K1: fused, time-blocked stencil + background kernel (full-resolution mode, Gaussian k <= 5).
 //
 // One CTA owns a 128x64 pixel tile of one stream and walks the T frames of the call in order:
-//   BGR tile + 2 px halo --(128-bit/32-bit coalesced loads)--> gray bytes in shared memory
-//   --> horizontal then vertical 8.8 fixed-point Gaussian on packed 2x16-bit lanes (registers)
+//   BGR tile + 2 px halo --(TMA, double buffered)--> gray bytes in shared memory
+//   --> horizontal 8.8 fixed-point Gaussian pass as a banded (Toeplitz) u8 x u8 matrix product on the
+//       tensor cores (IMMA.16832.U8: A = 16 gray rows x 32 columns via LDSM, B = the taps), sums packed
+//       2x16-bit into shared memory
+//   --> vertical pass on the packed lanes in registers (sliding 5-row window)
 //   --> polygon mask --> bg8 = rne(f32(bg)), |blur - bg8| > threshold --> bit-packed mask out
 //   --> bg = fma(bg, 1-alpha, rn(blur*alpha))
 // Each thread keeps the float64 background of its 4x8 pixels in registers across all T frames,
@@ -21,6 +24,8 @@
 #define FT_H 64
 #define FG_WORDS 36        // gray words per shared row: cols x0-4 .. x0+139 (18 units of 8 pixels)
 #define FG_ROWS 68         // rows y0-2 .. y0+65
+#define FH_ROWS 80          // 5 blocks of 16 rows: the tensor-core pass needs no row guards (rows 68..79 are scratch)
+#define FH_WORDS 68         // packed horizontal sums per shared row: 64 pixel pairs + 4 (bank spread for the D-fragment stores)
 #define FUSED_THREADS 256
 #define RAW_PITCH 432      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+415 (TMA box of 108 u32)
 #define RAW_BYTES (RAW_PITCH * FG_ROWS)                 // bytes one TMA box delivers
@@ -73,16 +78,27 @@ struct FusedParams {
 __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
     // 4 BGR pixels in 3 words -> 4 gray bytes.  Y = (3735 B + 19235 G + 9798 R + 16384) >> 15 computed as
     // (7470 B + 38470 G + 19596 R + 32768) >> 16 with two 16-bit x 8-bit dot products per pixel (IDP.2A);
-    // the result is byte 2 of the accumulator.
-    const uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u;              // bytes [B,G,R,x]
-    const uint32_t C_xB = 7470u << 16, C_GR = 38470u | (19596u << 16);       // bytes [x,B,G,R]
-    uint32_t p1 = __funnelshift_r(w0, w1, 24);                               // [B1,G1,R1,B2]
-    uint32_t p2 = __funnelshift_r(w1, w2, 16);                               // [B2,G2,R2,B3]
-    uint32_t t0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, 32768u));
-    uint32_t t1 = __dp2a_hi(C_R, p1, __dp2a_lo(C_BG, p1, 32768u));
-    uint32_t t2 = __dp2a_hi(C_R, p2, __dp2a_lo(C_BG, p2, 32768u));
+    // the lo/hi byte-pair selection of IDP.2A picks each pixel's bytes straight out of the three words.
+    // The result is byte 2 of the accumulator.
+    const uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u;              // byte pairs [B,G], [R,x]
+    const uint32_t C_xB = 7470u << 16, C_GR = 38470u | (19596u << 16);       // byte pairs [x,B], [G,R]
+    uint32_t t0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, 32768u));           // w0 = [B0,G0,R0,B1]
+    uint32_t t1 = __dp2a_hi(C_xB, w0, __dp2a_lo(C_GR, w1, 32768u));          // w1 = [G1,R1,B2,G2]
+    uint32_t t2 = __dp2a_hi(C_BG, w1, __dp2a_lo(C_R, w2, 32768u));           // w2 = [R2,B3,G3,R3]
     uint32_t t3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_xB, w2, 32768u));
     return __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);
+}
+
+// ---- tensor-core primitives for the horizontal pass ----
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void imma_u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
 __device__ __forceinline__ double u8_to_f64(uint32_t v) {
@@ -109,35 +125,37 @@ __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
     return x;
 }
 
-// One thread: 12 gray rows in -> 8 output rows x 4 pixels: blur, mask, threshold bits, background update.
-// INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels.
+// One thread: 12 rows of packed horizontal sums in -> 8 output rows x 4 pixels: vertical pass, mask, threshold
+// bits, background update.
+// INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels;
+// SH8: k = 5 (taps 1,4,6,4,1 compiled in, final shift 8 done by byte selection).
 template <bool KEEP, bool SAFE, bool INIT, bool MASKED, bool SH8>
-__device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)[32], uint32_t M, const FusedParams &p,
+__device__ __forceinline__ uint32_t fused_rows(const uint32_t *shw, double (&bg)[32], uint32_t M, const FusedParams &p,
                                                uint8_t *blur_out, int rows_valid) {
     const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
     const int qoff = 0x4B400000 - p.threshold;
     const unsigned thr2 = 2u * (unsigned)p.threshold;
+    const double nC = -(4503599627370496.0 * p.alpha);
     uint32_t win[5][2];
     uint32_t bits = 0;
 #pragma unroll
     for (int rr = 0; rr < 12; rr++) {
-        uint32_t W0 = sgw[rr * FG_WORDS], W1 = sgw[rr * FG_WORDS + 1], W2 = sgw[rr * FG_WORDS + 2];
-        uint32_t Ea = __byte_perm(W0, 0, 0x4342), Eb = __byte_perm(W1, 0, 0x4140);
-        uint32_t Ec = __byte_perm(W1, 0, 0x4342), Ed = __byte_perm(W2, 0, 0x4140);
-        uint32_t Oa = __funnelshift_r(Ea, Eb, 16), Ob = __funnelshift_r(Eb, Ec, 16), Oc = __funnelshift_r(Ec, Ed, 16);
-        uint32_t h0 = b0 * (Ea + Ec) + b1 * (Oa + Ob) + b2 * Eb;
-        uint32_t h1 = b0 * (Eb + Ed) + b1 * (Ob + Oc) + b2 * Ec;
+        const uint2 hv = *reinterpret_cast<const uint2 *>(shw + rr * FH_WORDS);    // pixels (0,1) and (2,3), 16 bits each
 #pragma unroll
         for (int i = 0; i < 4; i++) { win[i][0] = win[i + 1][0]; win[i][1] = win[i + 1][1]; }
-        win[4][0] = h0;
-        win[4][1] = h1;
+        win[4][0] = hv.x;
+        win[4][1] = hv.y;
         if (rr >= 4) {
             const int r = rr - 4;          // output row of this thread
             uint32_t v[2];      // the two pixels of a pair in bits [0,8) and [16,24) (SH8: in bytes 1 and 3)
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
-                v[j] = SH8 ? a : ((a >> p.shift) & 0x00FF00FFu);
+                if (SH8) {
+                    v[j] = (win[0][j] + win[4][j] + 0x00800080u) + 4u * (win[1][j] + win[3][j]) + 6u * win[2][j];
+                } else {
+                    uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
+                    v[j] = (a >> p.shift) & 0x00FF00FFu;
+                }
             }
             if (KEEP) {
                 if (r < rows_valid) {
@@ -155,11 +173,22 @@ __device__ __forceinline__ uint32_t fused_rows(const uint32_t *sgw, double (&bg)
                 uint32_t sv = SH8 ? __byte_perm(v[c >> 1], 0, (c & 1) ? 0x4443 : 0x4441)
                                   : ((c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu));
                 if (MASKED && (M & (1u << idx))) sv = 0;          // mask_off_areas paints BLACK into blur
-                const double sd = u8_to_f64(sv);
-                if (INIT) bg[idx] = sd;                           // ref_frame = blur.astype(float)
-                int q = bg8_magic<SAFE>(bg[idx]);
-                if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;   // |bg8 - blur| > threshold
-                bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
+                if (SAFE) {
+                    // rn(blur * alpha) without an int -> double conversion (the XU pipe converts 16 lanes/clk/SM):
+                    // X = 2^52 + blur is assembled from its bit pattern, and X * alpha - 2^52 * alpha is exactly
+                    // blur * alpha before the single rounding of the FMA (2^52 * alpha is exact).
+                    const double X = __hiloint2double(0x43300000, (int)sv);
+                    if (INIT) bg[idx] = X - 4503599627370496.0;   // ref_frame = blur.astype(float)
+                    int q = bg8_magic<SAFE>(bg[idx]);
+                    if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;   // |bg8 - blur| > threshold
+                    bg[idx] = __fma_rn(bg[idx], p.beta, __fma_rn(X, p.alpha, nC));
+                } else {
+                    const double sd = u8_to_f64(sv);
+                    if (INIT) bg[idx] = sd;
+                    int q = bg8_magic<SAFE>(bg[idx]);
+                    if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;
+                    bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
+                }
             }
         }
     }
@@ -170,8 +199,9 @@ template <bool KEEP, bool SAFE>
 __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constant__ CUtensorMap tmap, FusedParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     unsigned char *raw = fsm;                                                  // [2][RAW_STAGE] staged BGR rows (TMA)
-    uint32_t *sg2 = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);       // [2][FG_ROWS][FG_WORDS] gray, double buffered
-    uint64_t *bars = reinterpret_cast<uint64_t *>(fsm + 2 * RAW_STAGE + 2 * FG_ROWS * FG_WORDS * 4);
+    uint32_t *sg = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);        // [FH_ROWS][FG_WORDS] gray bytes (FG_ROWS used)
+    uint32_t *sh = sg + FH_ROWS * FG_WORDS;                                  // [FH_ROWS][FH_WORDS] packed horizontal sums
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sh + FH_ROWS * FH_WORDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.y;
     const int tile = blockIdx.x;
@@ -220,11 +250,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
         tma_load_4d(raw, &tmap, &bars[0], cx, cy, p.t0, s);
     }
     uint32_t *tw = p.tbits + ((size_t)s * p.Ttot + p.t0) * p.flatwords;
+    // B fragments of the horizontal pass (constant): the banded tap matrix for the two 8-column output blocks
+    // of a 32-byte window.  Output column n of block nb is gray byte 4 + 16 j + 8 nb + n of its row, window
+    // byte k is gray byte 16 j + k, so the tap index is k - n - 8 nb - 2 (taps b0 b1 b2 b1 b0).
+    uint32_t bfr[2][2];
+    {
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int idx = 16 * r + 4 * tq + i - g - 8 * nb - 2;
+                    const int tap = (idx == 2) ? p.b2 : (idx == 1 || idx == 3) ? p.b1 : (idx == 0 || idx == 4) ? p.b0 : 0;
+                    v |= (uint32_t)tap << (8 * i);
+                }
+                bfr[nb][r] = v;
+            }
+    }
+    // A-fragment row addresses of LDSM.x4 (lane L supplies row L&7 of matrix L>>3; matrices: rows 0-7 / 8-15 of
+    // bytes 0-15, then of bytes 16-31) and D-fragment store positions
+    const uint32_t sg_lane = smem_u32(sg) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * (FG_WORDS * 4) + 16 * warp + 16 * (lane >> 4);
+    uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * warp + (lane & 3);
 
     for (int t = 0; t < p.T; t++) {
-        // No barrier here: gray is double buffered, and every thread that gets this far has passed the barrier
-        // of frame t-1, i.e. all conversions out of raw stage (t+1)&1 (frame t-1) are complete.
-        uint32_t *sg = sg2 + (t & 1) * (FG_ROWS * FG_WORDS);
+        // No barrier here: every thread that gets this far has passed the second barrier of frame t-1, i.e. all
+        // conversions out of raw stage (t+1)&1 (frame t-1) and all reads of the gray plane are complete.
         if (tid == 0 && t + 1 < p.T) {
             mbar_expect_tx(&bars[(t + 1) & 1], RAW_BYTES);
             tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, p.t0 + t + 1, s);
@@ -273,8 +326,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
                         sg[(ry + 2) * FG_WORDS + ux + 1];
             }
         }
-        // ---- separable blur on packed pairs, sliding 5-row window, then the temporal update ----
-        const uint32_t *sgw = sg + (8 * warp) * FG_WORDS + lane;
+        // ---- horizontal pass on the tensor cores: warp = one 16-column window, 5 blocks of 16 rows ----
+        {
+            uint32_t a[5][4];
+#pragma unroll
+            for (int mb = 0; mb < 5; mb++) ldsm_x4(sg_lane + mb * (16 * FG_WORDS * 4), a[mb][0], a[mb][1], a[mb][2], a[mb][3]);
+#pragma unroll
+            for (int mb = 0; mb < 5; mb++) {
+                int d0[4], d1[4];
+                imma_u8(d0, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[0][0], bfr[0][1]);
+                imma_u8(d1, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[1][0], bfr[1][1]);
+                uint32_t *o = sh_lane + mb * (16 * FH_WORDS);
+                o[0] = __byte_perm(d0[0], d0[1], 0x5410);
+                o[4] = __byte_perm(d1[0], d1[1], 0x5410);
+                o[8 * FH_WORDS] = __byte_perm(d0[2], d0[3], 0x5410);
+                o[8 * FH_WORDS + 4] = __byte_perm(d1[2], d1[3], 0x5410);
+            }
+        }
+        __syncthreads();
+        // ---- vertical pass on packed pairs, sliding 5-row window, then the temporal update ----
+        const uint32_t *sgw = sh + (8 * warp) * FH_WORDS + 2 * lane;
         uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.Ttot + p.t0 + t) * h + py) * w + px : nullptr;
         const bool okx = px < w;
         uint32_t bits;
@@ -339,7 +410,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-#define FUSED_SMEM (2 * RAW_STAGE + 2 * FG_ROWS * FG_WORDS * 4 + 16)
+#define FUSED_SMEM (2 * RAW_STAGE + FH_ROWS * FG_WORDS * 4 + FH_ROWS * FH_WORDS * 4 + 16)
 
 int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st, int t0,
                     int Th, int force_bg) {
