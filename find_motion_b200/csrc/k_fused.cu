@@ -1,6 +1,6 @@
 // K1: fused, time-blocked stencil + background kernel (full-resolution mode, Gaussian k <= 5).
 //
-// One CTA owns a 128x64 pixel tile of one stream and walks the T frames of the call in order:
+// One CTA owns a 128 x FT_H pixel tile of one stream and walks the T frames of the call in order:
 //   BGR tile + 2 px halo --(TMA, double buffered)--> gray bytes in shared memory
 //   --> horizontal 8.8 fixed-point Gaussian pass as a banded (Toeplitz) u8 x u8 matrix product on the
 //       tensor cores (IMMA.16832.U8: A = 16 gray rows x 32 columns via LDSM, B = the taps), sums packed
@@ -8,7 +8,7 @@
 //   --> vertical pass on the packed lanes in registers (sliding 5-row window)
 //   --> polygon mask --> bg8 = rne(f32(bg)), |blur - bg8| > threshold --> bit-packed mask out
 //   --> bg = fma(bg, 1-alpha, rn(blur*alpha))
-// Each thread keeps the float64 background of its 4x8 pixels in registers across all T frames,
+// Each thread keeps the float64 background of its 4 x FT_RPT pixels in registers across all T frames,
 // so the background costs one 16 B/px HBM round trip per call instead of per frame.
 // Replaces blur_frame + mask_off_areas + find_diff's diff/threshold/accumulateWeighted
 // (find_motion/find_motion.py:487-494, 619-635, 246-257, 651-659).
@@ -21,10 +21,18 @@
 #include "fm_common.cuh"
 
 #define FT_W 128
-#define FT_H 64
+#ifndef FT_RPT
+#define FT_RPT 4           // rows per thread (a warp owns FT_RPT rows x 128 columns)
+#endif
+#define FT_H (8 * FT_RPT)  // tile height
+#define FT_PX (4 * FT_RPT) // pixels (and float64 background values) per thread
 #define FG_WORDS 36        // gray words per shared row: cols x0-4 .. x0+139 (18 units of 8 pixels)
-#define FG_ROWS 68         // rows y0-2 .. y0+65
-#define FH_ROWS 80          // 5 blocks of 16 rows: the tensor-core pass needs no row guards (rows 68..79 are scratch)
+#define FG_ROWS (FT_H + 4) // rows y0-2 .. y0+FT_H+1
+#define FH_MB ((FG_ROWS + 15) / 16)     // 16-row blocks of the tensor-core pass
+#define FH_ROWS (16 * FH_MB)            // rows of the shared planes (the rows past FG_ROWS are scratch: no row guards)
+#ifndef FUSED_MIN_CTAS
+#define FUSED_MIN_CTAS (FT_RPT == 4 ? 4 : 2)
+#endif
 #define FH_WORDS 68         // packed horizontal sums per shared row: 64 pixel pairs + 4 (bank spread for the D-fragment stores)
 #define FUSED_THREADS 256
 #define RAW_PITCH 432      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+415 (TMA box of 108 u32)
@@ -63,7 +71,7 @@ struct FusedParams {
     int t0, Ttot;               // they are frames t0 .. t0+T-1 of a Ttot-frame call (per-stream arrays have stride Ttot)
     int force_bg;               // the background is valid whatever the stream state says (second half of a call)
     int tilesX, tilesY;
-    double *bg;                 // [S][tiles][8 warps][8 rows][2 pairs][32 lanes] double2
+    double *bg;                 // [S][tiles][8 warps][FT_RPT rows][2 pairs][32 lanes] double2
     const uint32_t *maskbits;   // [S][h][wpr]
     uint32_t *tbits;            // [S][T][flatwords]  (row-padded == flat because w % 32 == 0)
     size_t flatwords;
@@ -113,6 +121,13 @@ __device__ __forceinline__ int bg8_magic(double b) {
     return __float_as_int(__fadd_rn(f, 12582912.0f));
 }
 
+// bits = 2 * bits + (d > thr2) in two instructions: d + ~thr2 carries out exactly when d > thr2 (unsigned), and the
+// carry is shifted into the accumulator by an add-with-carry.
+__device__ __forceinline__ void push_gt(uint32_t &bits, uint32_t d, uint32_t nthr2) {
+    uint32_t tmp;
+    asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits), "=r"(tmp) : "r"(d), "r"(nthr2));
+}
+
 // 8x8 transpose of 4-bit elements across the 8 lanes of a lane octet: in: lane i holds e[r] (nibble r)
 // = bits of row r; out: lane r holds nibble i = bits of lane i  -> a 32-pixel row word.
 __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
@@ -125,21 +140,21 @@ __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
     return x;
 }
 
-// One thread: 12 rows of packed horizontal sums in -> 8 output rows x 4 pixels: vertical pass, mask, threshold
+// One thread: FT_RPT + 4 rows of packed horizontal sums in -> FT_RPT output rows x 4 pixels: vertical pass, mask, threshold
 // bits, background update.
 // INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels;
 // SH8: k = 5 (taps 1,4,6,4,1 compiled in, final shift 8 done by byte selection).
 template <bool KEEP, bool SAFE, bool INIT, bool MASKED, bool SH8>
-__device__ __forceinline__ uint32_t fused_rows(const uint32_t *shw, double (&bg)[32], uint32_t M, const FusedParams &p,
+__device__ __forceinline__ uint32_t fused_rows(const uint32_t *shw, double (&bg)[FT_PX], uint32_t M, const FusedParams &p,
                                                uint8_t *blur_out, int rows_valid) {
     const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
     const int qoff = 0x4B400000 - p.threshold;
-    const unsigned thr2 = 2u * (unsigned)p.threshold;
+    const unsigned nthr2 = ~(2u * (unsigned)p.threshold);
     const double nC = -(4503599627370496.0 * p.alpha);
     uint32_t win[5][2];
     uint32_t bits = 0;
 #pragma unroll
-    for (int rr = 0; rr < 12; rr++) {
+    for (int rr = 0; rr < FT_RPT + 4; rr++) {
         const uint2 hv = *reinterpret_cast<const uint2 *>(shw + rr * FH_WORDS);    // pixels (0,1) and (2,3), 16 bits each
 #pragma unroll
         for (int i = 0; i < 4; i++) { win[i][0] = win[i + 1][0]; win[i][1] = win[i + 1][1]; }
@@ -180,23 +195,23 @@ __device__ __forceinline__ uint32_t fused_rows(const uint32_t *shw, double (&bg)
                     const double X = __hiloint2double(0x43300000, (int)sv);
                     if (INIT) bg[idx] = X - 4503599627370496.0;   // ref_frame = blur.astype(float)
                     int q = bg8_magic<SAFE>(bg[idx]);
-                    if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;   // |bg8 - blur| > threshold
+                    push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);           // |bg8 - blur| > threshold
                     bg[idx] = __fma_rn(bg[idx], p.beta, __fma_rn(X, p.alpha, nC));
                 } else {
                     const double sd = u8_to_f64(sv);
                     if (INIT) bg[idx] = sd;
                     int q = bg8_magic<SAFE>(bg[idx]);
-                    if ((unsigned)(q - qoff - (int)sv) > thr2) bits |= 1u << idx;
+                    push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);
                     bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
                 }
             }
         }
     }
-    return bits;
+    return __brev(bits) >> (32 - FT_PX);      // the first pixel was pushed first: bit idx = pixel 4r+c
 }
 
 template <bool KEEP, bool SAFE>
-__global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constant__ CUtensorMap tmap, FusedParams p) {
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const __grid_constant__ CUtensorMap tmap, FusedParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     unsigned char *raw = fsm;                                                  // [2][RAW_STAGE] staged BGR rows (TMA)
     uint32_t *sg = reinterpret_cast<uint32_t *>(fsm + 2 * RAW_STAGE);        // [FH_ROWS][FG_WORDS] gray bytes (FG_ROWS used)
@@ -211,14 +226,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     const bool border = (x0 == 0) || (x0 + FT_W >= w) || (y0 == 0) || (y0 + FT_H >= h);
     const bool has_bg = p.force_bg || p.state[s].has_bg != 0;
 
-    // this thread's pixels: columns x0 + 4*lane .. +3, rows y0 + 8*warp .. +7
-    const int px = x0 + 4 * lane, py = y0 + 8 * warp;
+    // this thread's pixels: columns x0 + 4*lane .. +3, rows y0 + FT_RPT*warp .. +FT_RPT-1
+    const int px = x0 + 4 * lane, py = y0 + FT_RPT * warp;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) +
-                   ((((size_t)s * p.tilesX * p.tilesY + tile) * 8 + warp) * 16) * 32 + lane;
-    double bg[32];
+                   ((((size_t)s * p.tilesX * p.tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32 + lane;
+    double bg[FT_PX];
     if (has_bg) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < FT_PX / 2; i++) {
             double2 v = bgt[i * 32];
             bg[2 * i] = v.x;
             bg[2 * i + 1] = v.y;
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     uint32_t M = 0;
     if (px < w) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < FT_RPT; r++) {
             int y = py + r;
             if (y < h) {
                 uint32_t mw = __ldg(p.maskbits + ((size_t)s * h + y) * p.wpr + (px >> 5));
@@ -275,6 +290,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
     const uint32_t sg_lane = smem_u32(sg) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * (FG_WORDS * 4) + 16 * warp + 16 * (lane >> 4);
     uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * warp + (lane & 3);
 
+    uint32_t pend = 0;
     for (int t = 0; t < p.T; t++) {
         // No barrier here: every thread that gets this far has passed the second barrier of frame t-1, i.e. all
         // conversions out of raw stage (t+1)&1 (frame t-1) and all reads of the gray plane are complete.
@@ -326,13 +342,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
                         sg[(ry + 2) * FG_WORDS + ux + 1];
             }
         }
-        // ---- horizontal pass on the tensor cores: warp = one 16-column window, 5 blocks of 16 rows ----
+        // ---- horizontal pass on the tensor cores: warp = one 16-column window, FH_MB blocks of 16 rows ----
         {
-            uint32_t a[5][4];
+            uint32_t a[FH_MB][4];
 #pragma unroll
-            for (int mb = 0; mb < 5; mb++) ldsm_x4(sg_lane + mb * (16 * FG_WORDS * 4), a[mb][0], a[mb][1], a[mb][2], a[mb][3]);
+            for (int mb = 0; mb < FH_MB; mb++) ldsm_x4(sg_lane + mb * (16 * FG_WORDS * 4), a[mb][0], a[mb][1], a[mb][2], a[mb][3]);
 #pragma unroll
-            for (int mb = 0; mb < 5; mb++) {
+            for (int mb = 0; mb < FH_MB; mb++) {
                 int d0[4], d1[4];
                 imma_u8(d0, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[0][0], bfr[0][1]);
                 imma_u8(d1, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[1][0], bfr[1][1]);
@@ -345,7 +361,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
         }
         __syncthreads();
         // ---- vertical pass on packed pairs, sliding 5-row window, then the temporal update ----
-        const uint32_t *sgw = sh + (8 * warp) * FH_WORDS + 2 * lane;
+        const uint32_t *sgw = sh + (FT_RPT * warp) * FH_WORDS + 2 * lane;
         uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.Ttot + p.t0 + t) * h + py) * w + px : nullptr;
         const bool okx = px < w;
         uint32_t bits;
@@ -354,21 +370,38 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused(const __grid_constan
         else if (p.shift == 8) bits = fused_rows<KEEP, SAFE, false, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
         else bits = fused_rows<KEEP, SAFE, false, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
         // ---- 8 lanes x 8 rows of nibbles -> one 32-pixel word per lane, coalesced store ----
+#if FT_RPT == 4
+        // a thread has 4 rows: two frames share one transpose (rows 0-3 = frame t-1, rows 4-7 = frame t)
+        if (!(t & 1) && t + 1 < p.T) {
+            pend = bits;
+        } else {
+            const bool two = t & 1;
+            uint32_t word = nibble_transpose8(two ? (pend | (bits << 16)) : bits, lane);
+            const int rsel = lane & 7;
+            const int y = py + (rsel & 3);
+            const int xw = (x0 >> 5) + (lane >> 3);
+            const bool mine = two || rsel < 4;
+            uint32_t *dst = tw + (size_t)y * p.wpr + xw;
+            if (two && rsel < 4) dst -= p.flatwords;
+            if (mine && y < h && xw < p.wpr) *dst = word;
+        }
+#else
         uint32_t word = nibble_transpose8(bits, lane);
         {
             int y = py + (lane & 7);
             int xw = (x0 >> 5) + (lane >> 3);
             if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
         }
+#endif
         if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 8 rows hold something
             int *rr = p.rawrange + 2 * ((size_t)s * p.Ttot + p.t0 + t);
-            atomicMax(rr, min(py + 7, h - 1));
+            atomicMax(rr, min(py + FT_RPT - 1, h - 1));
             atomicMax(rr + 1, h - 1 - py);
         }
         tw += p.flatwords;
     }
 #pragma unroll
-    for (int i = 0; i < 16; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
+    for (int i = 0; i < FT_PX / 2; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
 }
 
 // tiled background -> row-major float64 plane
@@ -378,9 +411,9 @@ __global__ void k_bg_export_fused(const double *__restrict__ bg, double *__restr
     if (x >= w) return;
     int tx = x / FT_W, ty = y / FT_H, tile = ty * tilesX + tx;
     int lx = x - tx * FT_W, ly = y - ty * FT_H;
-    int warp = ly >> 3, r = ly & 7, lane = lx >> 2, c = lx & 3;
+    int warp = ly / FT_RPT, r = ly % FT_RPT, lane = lx >> 2, c = lx & 3;
     int idx = 4 * r + c;           // pixel index inside the thread
-    size_t base = ((((size_t)s * tilesX * tilesY + tile) * 8 + warp) * 16) * 32;
+    size_t base = ((((size_t)s * tilesX * tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32;
     dst[(size_t)y * w + x] = bg[(base + (size_t)(idx >> 1) * 32 + lane) * 2 + (idx & 1)];
 }
 
