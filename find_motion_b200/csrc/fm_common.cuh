@@ -51,13 +51,13 @@ struct fm_ctx {
     int maxc;
     // tables
     int *coef;                 // [k] 8.8 fixed-point Gaussian taps
-    uint4 *etab;               // [nd] taps packed 4 per word for the four output phases (IDP.4A blur)
+    uint2 *wtab;               // tap tables of the tensor-core blur (k_wide.cu): pass 1 then pass 2, [entries][32 lanes]
     ResizeTab xtab, ytab;
     int *g4start, *g4n, *g4off;   // x taps regrouped in 4-pixel groups with zero-weight padding (k_resize_gray_g4)
     float4 *g4w;
     // planes
     uint8_t *gray;             // [S][Tmax][h][w]
-    uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or two row-quad byte planes [2][S][Tmax][hq][w] u32
+    uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or the low/high byte planes of k_wide.cu
     uint8_t *blur;             // [S][Tmax][h][w]  masked blur
     double *bg;                // [S][ntiles][8][32][2]  float64 background, tiled
     uint32_t *maskbits;        // [S][h][wpr]  1 = zero the blur here
@@ -133,7 +133,9 @@ int fm_launch_bg_export(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st)
 int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st);
 int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t st);
 bool fm_fused_supported(const fm_ctx *c);
-int fm_blur_quads(const fm_ctx *c);
+size_t fm_wide_plane_bytes(const fm_ctx *c);
+int fm_wide_init(fm_ctx *c, const int *taps);
+int fm_launch_wide_blur(fm_ctx *c, int T, cudaStream_t st);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);

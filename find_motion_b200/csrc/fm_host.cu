@@ -121,7 +121,7 @@ static int upload_tab(ResizeTab *d, const HostTab &h) {
 extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
-    cudaFree(c->coef); cudaFree(c->etab);
+    cudaFree(c->coef); cudaFree(c->wtab);
     cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
@@ -240,22 +240,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     {
         std::vector<int> taps = gauss_coeffs(c->k);
         if ((rc = upload(&c->coef, taps))) return fail(rc);
-        // E[d][ph] byte b = c[4(d - D0) - ph + r + b]  (k_frontend.cu, wide-kernel Gaussian)
-        const int r = c->k >> 1, D0 = (r + 3) / 4 + 1, nd = 2 * D0 + 1;
-        std::vector<uint4> et(nd);
-        for (int d = 0; d < nd; d++) {
-            uint32_t e[4];
-            for (int ph = 0; ph < 4; ph++) {
-                uint32_t v = 0;
-                for (int b = 0; b < 4; b++) {
-                    int t = 4 * (d - D0) - ph + r + b;
-                    if (t >= 0 && t < c->k) v |= (uint32_t)(taps[t] & 255) << (8 * b);
-                }
-                e[ph] = v;
-            }
-            et[d] = make_uint4(e[0], e[1], e[2], e[3]);
-        }
-        if ((rc = upload(&c->etab, et))) return fail(rc);
+        if (!c->fused && (rc = fm_wide_init(c, taps.data()))) return fail(rc);
     }
 
     const size_t F = (size_t)c->S * c->Tmax;
@@ -273,7 +258,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     const bool need_planes = !c->fused || (cfg->flags & FM_FLAG_KEEP_PLANES);
     const bool need_hor = !c->fused;
     ALLOC(c->gray, need_planes ? F * c->N : 16);
-    ALLOC(c->hor, !need_hor ? 16 : std::max(F * c->N * sizeof(uint16_t), 2 * F * (size_t)(fm_blur_quads(c) + 4) * c->w * sizeof(uint32_t)));
+    ALLOC(c->hor, !need_hor ? 16 : std::max(F * c->N * sizeof(uint16_t), 2 * fm_wide_plane_bytes(c)));
     ALLOC(c->blur, need_planes ? F * c->N + 64 : 64);
     const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX, c->fused ? fm_fused_bg_doubles(c) : (size_t)0);
     ALLOC(c->bg, bg_doubles * sizeof(double));

@@ -432,162 +432,6 @@ __global__ void __launch_bounds__(256) k_vblur(const uint16_t *__restrict__ hor,
     blur[((size_t)f * h + y) * w + x] = (uint8_t)v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// wide-kernel Gaussian (k = 7 ... 1023): both passes on IDP.4A (4 taps per instruction).
-//
-// Horizontal: one thread = 4 consecutive pixels x 4 consecutive rows (a "quad" of rows).  The 16-bit
-// results of the 4 rows are split into low and high bytes and stored as two byte planes in which a
-// 32-bit word holds the SAME pixel of 4 consecutive rows ("row-quad packed"), so that the vertical
-// pass is the same 4-taps-per-instruction dot product along y:  ver = 256 * sum(c*hi) + sum(c*lo).
-// The planes are padded by r rows at the top (and >= r at the bottom) with the BORDER_REFLECT_101
-// rows materialised, so the vertical pass has no border logic.  Integer arithmetic: exact.
-//
-// E[d][ph] = taps c[4d' - ph + r + b], b = 0..3 packed in bytes, for word offset d' = d - D0 relative
-// to the word that holds output 4n, and output phase ph (position of the output inside its word).
-// ---------------------------------------------------------------------------------------------
-// a gray word that may straddle the image border (BORDER_REFLECT_101); single reflection when r < w
-__device__ __forceinline__ uint32_t load_gray_word(const uint8_t *row, int m, int w, bool small) {
-    int x = 4 * m;
-    if (x >= 0 && x + 3 < w) return __ldg(reinterpret_cast<const uint32_t *>(row + x));
-    uint32_t v = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        int i = x + b;
-        if (small) i = fm_reflect101(i, w);
-        else i = i < 0 ? -i : (i >= w ? 2 * w - 2 - i : i);
-        v |= (uint32_t)row[i] << (8 * b);
-    }
-    return v;
-}
-
-__device__ __forceinline__ void load_tap_table(uint4 *sE, const uint4 *__restrict__ etab, int nd) {
-    for (int d = threadIdx.x; d < nd; d += blockDim.x) sE[d] = __ldg(etab + d);
-    __syncthreads();
-}
-
-// grid: (ceil(w/4 / 128), hq, F)   hq = padded height / 4
-__global__ void __launch_bounds__(128) k_hblur_q(const uint8_t *__restrict__ gray, uint32_t *__restrict__ qlo,
-                                                 uint32_t *__restrict__ qhi, const uint4 *__restrict__ etab, int k,
-                                                 int w, int h, int hq, int hqa) {
-    extern __shared__ uint4 sE[];
-    const int r = k >> 1;
-    const int D0 = (r + 3) / 4 + 1, nd = 2 * D0 + 1;      // d' in [-D0, D0]
-    load_tap_table(sE, etab, nd);
-    const int f = blockIdx.z, Y = blockIdx.y;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;   // word index along x: outputs 4n .. 4n+3
-    if (4 * n >= w) return;
-    const uint8_t *rows[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) rows[i] = gray + ((size_t)f * h + fm_reflect101(4 * Y + i - r, h)) * w;
-    uint32_t acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int o = 0; o < 4; o++) acc[i][o] = 0;
-    const bool interior = (4 * (n - D0) >= 0) && (4 * (n + D0) + 3 < w);
-    if (interior) {
-#pragma unroll 2
-        for (int d = 0; d < nd; d++) {
-            uint4 e = sE[d];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t W = __ldg(reinterpret_cast<const uint32_t *>(rows[i]) + (n - D0 + d));
-                acc[i][0] = __dp4a(W, e.x, acc[i][0]);
-                acc[i][1] = __dp4a(W, e.y, acc[i][1]);
-                acc[i][2] = __dp4a(W, e.z, acc[i][2]);
-                acc[i][3] = __dp4a(W, e.w, acc[i][3]);
-            }
-        }
-    } else {
-        const bool small = r >= w;
-        for (int d = 0; d < nd; d++) {
-            uint4 e = sE[d];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t W = load_gray_word(rows[i], n - D0 + d, w, small);
-                acc[i][0] = __dp4a(W, e.x, acc[i][0]);
-                acc[i][1] = __dp4a(W, e.y, acc[i][1]);
-                acc[i][2] = __dp4a(W, e.z, acc[i][2]);
-                acc[i][3] = __dp4a(W, e.w, acc[i][3]);
-            }
-        }
-    }
-    // row-quad packing: word(x) = byte b of rows 0..3
-    uint32_t lo[4], hi[4];
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        uint32_t a01 = __byte_perm(acc[0][o], acc[1][o], 0x5140);   // [a0.b0, a1.b0, a0.b1, a1.b1]
-        uint32_t a23 = __byte_perm(acc[2][o], acc[3][o], 0x5140);
-        lo[o] = __byte_perm(a01, a23, 0x5410);
-        hi[o] = __byte_perm(a01, a23, 0x7632);
-    }
-    size_t base = ((size_t)f * hqa + Y + 2) * w + 4 * n;      // planes start 2 quads early (see k_vblur_q)
-    if (4 * n + 4 <= w) {
-        *reinterpret_cast<uint4 *>(qlo + base) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4 *>(qhi + base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    } else {
-        for (int o = 0; o < 4 && 4 * n + o < w; o++) { qlo[base + o] = lo[o]; qhi[base + o] = hi[o]; }
-    }
-}
-
-// grid: (ceil(w/128), ceil(h/8), F): one thread = one column, 8 output rows (two quads)
-__global__ void __launch_bounds__(128) k_vblur_q(const uint32_t *__restrict__ qlo, const uint32_t *__restrict__ qhi,
-                                                 uint8_t *__restrict__ blur, const uint4 *__restrict__ etab, int k, int w,
-                                                 int h, int hqa, int wpr, int T, const uint32_t *__restrict__ maskbits) {
-    extern __shared__ uint4 sE[];
-    const int r = k >> 1;
-    const int D0 = (r + 3) / 4 + 1, nd = 2 * D0 + 1;
-    load_tap_table(sE, etab, nd);
-    if (threadIdx.x == 0) sE[nd] = make_uint4(0, 0, 0, 0);
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    // output rows y0 .. y0+7 with y0 chosen so that the padded row y0 + r is quad aligned: output i then
-    // sits in quad Yb + (i >> 2) at phase i & 3 (compile-time), its table entry is E[d - (i >> 2)]
-    const int y0 = blockIdx.y * 8 - (r & 3);
-    const int Yb = (y0 + r) >> 2;
-    const bool live = x < w;
-    // quads Yb - D0 .. Yb + D0 + 1 are read without bounds checks: the planes carry 2 spare quads in front
-    // and enough behind, and every tap that falls outside the real rows has a zero coefficient
-    const uint32_t *plo = qlo + ((size_t)f * hqa + (Yb - D0 + 2)) * w + x;
-    const uint32_t *phi = qhi + ((size_t)f * hqa + (Yb - D0 + 2)) * w + x;
-    uint32_t alo[8], ahi[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { alo[i] = 0; ahi[i] = 0; }
-    uint4 e1 = make_uint4(0, 0, 0, 0);     // E[d-1]
-    __syncthreads();
-    if (!live) return;
-#pragma unroll 4
-    for (int d = 0; d < nd + 1; d++) {
-        uint4 e0 = sE[d];
-        uint32_t Wl = __ldg(plo), Wh = __ldg(phi);
-        plo += w;
-        phi += w;
-        alo[0] = __dp4a(Wl, e0.x, alo[0]); ahi[0] = __dp4a(Wh, e0.x, ahi[0]);
-        alo[1] = __dp4a(Wl, e0.y, alo[1]); ahi[1] = __dp4a(Wh, e0.y, ahi[1]);
-        alo[2] = __dp4a(Wl, e0.z, alo[2]); ahi[2] = __dp4a(Wh, e0.z, ahi[2]);
-        alo[3] = __dp4a(Wl, e0.w, alo[3]); ahi[3] = __dp4a(Wh, e0.w, ahi[3]);
-        alo[4] = __dp4a(Wl, e1.x, alo[4]); ahi[4] = __dp4a(Wh, e1.x, ahi[4]);
-        alo[5] = __dp4a(Wl, e1.y, alo[5]); ahi[5] = __dp4a(Wh, e1.y, ahi[5]);
-        alo[6] = __dp4a(Wl, e1.z, alo[6]); ahi[6] = __dp4a(Wh, e1.z, ahi[6]);
-        alo[7] = __dp4a(Wl, e1.w, alo[7]); ahi[7] = __dp4a(Wh, e1.w, ahi[7]);
-        e1 = e0;
-    }
-    const int s = f / T;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int y = y0 + i;
-        if (y >= 0 && y < h) {
-            int v = (int)((ahi[i] * 256u + alo[i] + 32768u) >> 16);
-            uint32_t m = maskbits[((size_t)s * h + y) * wpr + (x >> 5)];
-            if ((m >> (x & 31)) & 1) v = 0;
-            blur[((size_t)f * h + y) * w + x] = (uint8_t)v;
-        }
-    }
-}
-
-// quads of the padded row-quad planes: rows -r .. h-1+r (+3 so that the last outputs' quads exist)
-int fm_blur_quads(const fm_ctx *c) { return (c->h + 2 * (c->k >> 1) + 3) / 4 + 3; }
-
 int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
                        cudaStream_t st) {
     const int F = c->S * T;
@@ -657,22 +501,7 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         }
     }
     // separable blur
-    if (c->k >= 3 && (c->w % 4) == 0) {
-        const int r = c->k >> 1;
-        const int hq = fm_blur_quads(c), hqa = hq + 4;
-        const int nd = 2 * ((r + 3) / 4 + 1) + 1;
-        uint32_t *qlo = reinterpret_cast<uint32_t *>(c->hor);
-        uint32_t *qhi = qlo + (size_t)c->S * c->Tmax * hqa * c->w;
-        dim3 hgrid(((c->w + 3) / 4 + 127) / 128, hq, F);
-        k_hblur_q<<<hgrid, 128, (size_t)(nd + 1) * sizeof(uint4), st>>>(c->gray, qlo, qhi, c->etab, c->k, c->w, c->h,
-                                                                        hq, hqa);
-        FM_LAUNCH_CHECK();
-        dim3 vgrid((c->w + 127) / 128, (c->h + 3 + 7) / 8, F);
-        k_vblur_q<<<vgrid, 128, (size_t)(nd + 1) * sizeof(uint4), st>>>(qlo, qhi, c->blur, c->etab, c->k, c->w, c->h,
-                                                                        hqa, c->wpr, T, c->maskbits);
-        FM_LAUNCH_CHECK();
-        return FM_OK;
-    }
+    if (c->k >= 3 && (c->w % 4) == 0) return fm_launch_wide_blur(c, T, st);     // tensor-core blur (k_wide.cu)
     dim3 bgrid((c->w + 255) / 256, c->h, F);
     size_t sm = (size_t)c->k * sizeof(int);
     k_hblur<<<bgrid, 256, sm, st>>>(c->gray, c->hor, c->coef, c->k, c->w, c->h);
