@@ -51,7 +51,7 @@ struct fm_ctx {
     int maxc;
     // tables
     int *coef;                 // [k] 8.8 fixed-point Gaussian taps
-    uint2 *wtab;               // tap tables of the tensor-core blur (k_wide.cu): pass 1 then pass 2, [entries][32 lanes]
+    uint32_t *wtab;            // tap tables of the tensor-core blur (k_wide.cu): pass 1 (uint2 per lane) then pass 2 (uint4 per lane)
     ResizeTab xtab, ytab;
     int *g4start, *g4n, *g4off;   // x taps regrouped in 4-pixel groups with zero-weight padding (k_resize_gray_g4)
     float4 *g4w;
@@ -135,7 +135,7 @@ int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t 
 bool fm_fused_supported(const fm_ctx *c);
 size_t fm_wide_plane_bytes(const fm_ctx *c);
 int fm_wide_init(fm_ctx *c, const int *taps);
-int fm_launch_wide_blur(fm_ctx *c, int T, cudaStream_t st);
+int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);

@@ -432,13 +432,21 @@ __global__ void __launch_bounds__(256) k_vblur(const uint16_t *__restrict__ hor,
     blur[((size_t)f * h + y) * w + x] = (uint8_t)v;
 }
 
+int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
+    dim3 grid(((c->N + 3) / 4 + 255) / 256, c->S * T);
+    k_gray<<<grid, 256, 0, st>>>(frames, sstride, fstride, T, c->N, c->gray);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
 int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
                        cudaStream_t st) {
     const int F = c->S * T;
+    const bool wide = c->k >= 3 && (c->w % 4) == 0;      // tensor-core blur (k_wide.cu)
+    if (c->resize_mode == 0 && wide) return fm_launch_wide_blur(c, frames, sstride, fstride, T, st);   // gray fused into pass 1
     if (c->resize_mode == 0) {
-        dim3 grid(((c->N + 3) / 4 + 255) / 256, F);
-        k_gray<<<grid, 256, 0, st>>>(frames, sstride, fstride, T, c->N, c->gray);
-        FM_LAUNCH_CHECK();
+        int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
+        if (rc) return rc;
     } else {
         K0Params p;
         p.frames = frames; p.sstride = sstride; p.fstride = fstride;
@@ -501,7 +509,7 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         }
     }
     // separable blur
-    if (c->k >= 3 && (c->w % 4) == 0) return fm_launch_wide_blur(c, T, st);     // tensor-core blur (k_wide.cu)
+    if (wide) return fm_launch_wide_blur(c, nullptr, 0, 0, T, st);
     dim3 bgrid((c->w + 255) / 256, c->h, F);
     size_t sm = (size_t)c->k * sizeof(int);
     k_hblur<<<bgrid, 256, sm, st>>>(c->gray, c->hor, c->coef, c->k, c->w, c->h);

@@ -11,25 +11,36 @@
 //     plane[frame][group of 32 padded rows][half][column][4 words],   word (4*half + j) byte i = row j' + 8 i of
 //   the group (j' = 4*half + j), i.e. the 16 bytes of a (column, half) are one ldmatrix row.
 //   Padded row p holds image row reflect101(p - r), so pass 2 has no border logic.
+//   In full-resolution mode the BGR -> gray conversion (fm.py:493) is fused into the staging of
+//   the shared tile, so no gray plane is written or read.
 // Pass 2 (k_wide_v), vertical: out[y][x] = (256 * sum_j hi[y + j][x] c[j] + sum_j lo[y + j][x] c[j] + 32768) >> 16.
-//   A = 16 columns x 32 padded rows of a byte plane (one ldmatrix.x4 per plane), B = the taps with the k index
-//   permuted to the row order of the plane words (k = 4t+i <-> row t + 8i, k = 16+4t+i <-> row 4 + t + 8i).
-//   Epilogue: transpose through shared memory, apply the polygon mask bits, store 32 bytes per lane.
+//   A = the taps as a banded 16 x 32 block with the k index permuted to the row order of the plane words
+//   (k = 4t+i <-> row t + 8i, k = 16+4t+i <-> row 4 + t + 8i), B = 32 padded rows x 8 columns of a byte plane
+//   (ldmatrix.x4 = two column blocks).  The columns of a block are permuted (block nb holds columns
+//   8t' + 2nb + e) so that a thread ends up with 8 consecutive output bytes of a row: mask, two 32-bit stores.
+//   The planes stream through a cp.async double buffer along a strip of column tiles.
 #include "fm_common.cuh"
 
-#define WH_COLS 128        // pass 1 CTA tile: 32 padded rows (one group) x 128 columns, warp = 32 x 32
-#define WV_ROWS 128        // pass 2 CTA tile: 128 output rows x 32 columns, warp = 32 x 32
+#define WH_COLS 256        // pass 1 CTA tile: 32 padded rows (one group) x 256 columns, 8 warps of 32 x 32
+#define WH_THREADS 256
+#define WV_ROWS 128        // pass 2 CTA tile: 128 output rows x 32 columns per step, 4 warps of 32 x 32
 #define WV_COLS 32
+#define WV_NT 4            // column tiles per pass-2 CTA (cp.async double buffer)
 
 __device__ __forceinline__ uint32_t wsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void wldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void wimma(int (&d)[4], const uint32_t (&a)[4], uint2 b) {
+__device__ __forceinline__ void wimma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                      uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void wcp_async16(uint32_t dst, const void *src, bool valid) {
+    const int n = valid ? 16 : 0;                 // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
 struct WideGeom {
@@ -59,65 +70,101 @@ size_t fm_wide_plane_bytes(const fm_ctx *c) {
     return (size_t)c->S * c->Tmax * g.NGa * 2 * c->w * 16;          // one byte plane
 }
 
-// Tap tables: entry d = 4 s - nb + 3 (s = window step, nb = 8-wide output block), lane (g = lane >> 2, t = lane & 3),
-// two registers of 4 taps.  Pass 1: tap index 8 (d - 3) + kk - g + r - R16, kk = 16 reg + 4 t + i.
-// Pass 2: tap index 8 (d - 3) + row(kk) - g with the plane's row order.
+// Tap tables, per lane (g = lane >> 2, t = lane & 3).
+// Pass 1 (B operand, uint2): entry d = 4 s - nb + 3 (s = window step, nb = 8-column output block); register rg
+//   byte i is the tap 8 (d - 3) + kk - g + r - R16 with kk = 16 rg + 4 t + i.
+// Pass 2 (A operand, uint4): entry e = 2 s - mt + 1 (s = row group of the window, mt = 16-row output tile);
+//   registers a0..a3 = (m = g, g+8, g, g+8; k = 4t+i, 4t+i, 16+4t+i, 16+4t+i), tap 16 (e - 1) + row(k) - m.
 int fm_wide_init(fm_ctx *c, const int *taps) {
     WideGeom g = wide_geom(c);
-    const int nh = 4 * g.Sh + 3, nv = 4 * g.Sv + 3;
-    uint2 *hh = (uint2 *)malloc((size_t)(nh + nv) * 32 * sizeof(uint2));
+    const int nh = 4 * g.Sh + 3, nv = 2 * g.Sv;
+    const size_t words = (size_t)nh * 32 * 2 + (size_t)nv * 32 * 4;
+    uint32_t *hh = (uint32_t *)malloc(words * 4);
     if (!hh) { fm_set_error("out of host memory"); return FM_ENOMEM; }
-    uint2 *hv = hh + (size_t)nh * 32;
-    for (int pass = 0; pass < 2; pass++) {
-        uint2 *tab = pass ? hv : hh;
-        const int n = pass ? nv : nh;
-        for (int d = 0; d < n; d++)
-            for (int lane = 0; lane < 32; lane++) {
-                const int gq = lane >> 2, t = lane & 3;
-                uint32_t reg[2] = {0, 0};
-                for (int rg = 0; rg < 2; rg++)
-                    for (int i = 0; i < 4; i++) {
-                        int j;
-                        if (pass == 0) j = 8 * (d - 3) + (16 * rg + 4 * t + i) - gq + g.r - g.R16;
-                        else j = 8 * (d - 3) + (4 * rg + t + 8 * i) - gq;
-                        if (j >= 0 && j < g.k) reg[rg] |= (uint32_t)(taps[j] & 255) << (8 * i);
-                    }
-                tab[(size_t)d * 32 + lane] = make_uint2(reg[0], reg[1]);
+    uint32_t *hv = hh + (size_t)nh * 32 * 2;
+    auto tap = [&](int j) -> uint32_t { return (j >= 0 && j < g.k) ? (uint32_t)(taps[j] & 255) : 0u; };
+    for (int d = 0; d < nh; d++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int gq = lane >> 2, t = lane & 3;
+            for (int rg = 0; rg < 2; rg++) {
+                uint32_t v = 0;
+                for (int i = 0; i < 4; i++) v |= tap(8 * (d - 3) + (16 * rg + 4 * t + i) - gq + g.r - g.R16) << (8 * i);
+                hh[((size_t)d * 32 + lane) * 2 + rg] = v;
             }
-    }
-    cudaError_t e = cudaMalloc((void **)&c->wtab, (size_t)(nh + nv) * 32 * sizeof(uint2));
-    if (e == cudaSuccess) e = cudaMemcpy(c->wtab, hh, (size_t)(nh + nv) * 32 * sizeof(uint2), cudaMemcpyHostToDevice);
+        }
+    for (int e = 0; e < nv; e++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int gq = lane >> 2, t = lane & 3;
+            for (int a = 0; a < 4; a++) {
+                const int m = gq + 8 * (a & 1), half = a >> 1;
+                uint32_t v = 0;
+                for (int i = 0; i < 4; i++) v |= tap(16 * (e - 1) + (4 * half + t + 8 * i) - m) << (8 * i);
+                hv[((size_t)e * 32 + lane) * 4 + a] = v;
+            }
+        }
+    cudaError_t er = cudaMalloc((void **)&c->wtab, words * 4);
+    if (er == cudaSuccess) er = cudaMemcpy(c->wtab, hh, words * 4, cudaMemcpyHostToDevice);
     free(hh);
-    if (e != cudaSuccess) { fm_set_error("wide-blur tap tables: %s", cudaGetErrorString(e)); return FM_ECUDA; }
+    if (er != cudaSuccess) { fm_set_error("wide-blur tap tables: %s", cudaGetErrorString(er)); return FM_ECUDA; }
     return FM_OK;
 }
 
-// grid: (ceil(w / 128), NGa, F), 128 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
-__global__ void __launch_bounds__(128) k_wide_h(const uint8_t *__restrict__ gray, uint32_t *__restrict__ plo,
-                                                uint32_t *__restrict__ phi, const uint2 *__restrict__ tabg, int w, int h,
-                                                int r, int R16, int Sh, int pitch, int NGa) {
+__device__ __forceinline__ uint32_t wgray1(const uint8_t *p) {
+    return (3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15;
+}
+__device__ __forceinline__ uint32_t wgray4(uint32_t w0, uint32_t w1, uint32_t w2) {
+    // 4 BGR pixels in 3 words -> 4 gray bytes (two IDP.2A per pixel on doubled coefficients; Y is byte 2 of the sum)
+    const uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u;
+    const uint32_t C_xB = 7470u << 16, C_GR = 38470u | (19596u << 16);
+    uint32_t t0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, 32768u));
+    uint32_t t1 = __dp2a_hi(C_xB, w0, __dp2a_lo(C_GR, w1, 32768u));
+    uint32_t t2 = __dp2a_hi(C_BG, w1, __dp2a_lo(C_R, w2, 32768u));
+    uint32_t t3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_xB, w2, 32768u));
+    return __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);
+}
+
+// grid: (ceil(w / 256), NGa, F), 256 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
+// BGR: src = the caller's frames (identity resize, 4-byte aligned rows); otherwise src = the gray plane [F][h][w].
+template <bool BGR>
+__global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
+                                                       uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
+                                                       const uint2 *__restrict__ tabg, int w, int h, int r, int R16, int Sh,
+                                                       int pitch, int NGa) {
     extern __shared__ __align__(16) unsigned char wsm[];
     unsigned char *tile = wsm;                                              // [32][pitch] gray bytes
     uint2 *tab = reinterpret_cast<uint2 *>(wsm + 32 * pitch);             // [4 Sh + 3][32]
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
-    for (int i = tid; i < (4 * Sh + 3) * 32; i += 128) tab[i] = __ldg(tabg + i);
+    for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
     // stage the window: shared column cc <-> image column X0 - R16 + cc (reflected), row rr <-> padded row 32 G + rr
     {
         const int words = pitch >> 2;
-        const uint8_t *fr = gray + (size_t)f * h * w;
-        for (int i = tid; i < 32 * words; i += 128) {
-            const int rr = i / words, cw = i - rr * words;
-            const uint8_t *row = fr + (size_t)fm_reflect101(32 * G + rr - r, h) * w;
-            const int x = X0 - R16 + 4 * cw;
-            uint32_t v;
-            if (x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-            else {
-                v = 0;
+        const uint8_t *fr = BGR ? src + (size_t)(f / T) * sstride + (size_t)(f % T) * fstride : src + (size_t)f * h * w;
+        const int px = BGR ? 3 : 1;
+#pragma unroll 1
+        for (int rr = wq; rr < 32; rr += WH_THREADS / 32) {
+            const uint8_t *row = fr + (size_t)fm_reflect101(32 * G + rr - r, h) * w * px;
+            uint32_t *trow = reinterpret_cast<uint32_t *>(tile + rr * pitch);
+            for (int cw = lane; cw < words; cw += 32) {
+                const int x = X0 - R16 + 4 * cw;
+                uint32_t v;
+                if (x >= 0 && x + 3 < w) {
+                    if (BGR) {
+                        const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 3 * x);
+                        v = wgray4(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+                    } else {
+                        v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+                    }
+                } else {
+                    v = 0;
 #pragma unroll
-                for (int b = 0; b < 4; b++) v |= (uint32_t)row[fm_reflect101(x + b, w)] << (8 * b);
+                    for (int b = 0; b < 4; b++) {
+                        const int xx = fm_reflect101(x + b, w);
+                        v |= (BGR ? wgray1(row + 3 * xx) : (uint32_t)row[xx]) << (8 * b);
+                    }
+                }
+                trow[cw] = v;
             }
-            *reinterpret_cast<uint32_t *>(tile + rr * pitch + 4 * cw) = v;
         }
     }
     __syncthreads();
@@ -136,8 +183,8 @@ __global__ void __launch_bounds__(128) k_wide_h(const uint8_t *__restrict__ gray
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             const uint2 b = tab[(4 * s - nb + 3) * 32 + lane];
-            wimma(acc[0][nb], a0, b);
-            wimma(acc[1][nb], a1, b);
+            wimma(acc[0][nb], a0[0], a0[1], a0[2], a0[3], b.x, b.y);
+            wimma(acc[1][nb], a1[0], a1[1], a1[2], a1[3], b.x, b.y);
         }
     }
     // thread (g, t): rows g, g+8 (tile 0), g+16, g+24 (tile 1) of columns 2t, 2t+1 of each block = word g of the group
@@ -158,109 +205,159 @@ __global__ void __launch_bounds__(128) k_wide_h(const uint8_t *__restrict__ gray
         }
 }
 
-// grid: (ceil(w / 32), ceil(h / 128), F), 128 threads.
-// dynamic smem: 2 planes * (4 + Sv - 1) groups * 2 halves * 32 columns * 16 B  +  (4 Sv + 3) * 256  +  4 * 1024
+// shared slot of column c of a 32-column tile: the 8 columns {8t' + 2nb + e} of a block land in 8 different 16-byte lanes
+__device__ __forceinline__ int wv_slot(int c) { return (c & 24) | ((c & 7) ^ (((c >> 3) & 3) << 1)); }
+
+// grid: (ceil(w / (32 WV_NT)), ceil(h / 128), F), 128 threads.
+// dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 32 columns * 16 B  +  2 Sv * 512
 __global__ void __launch_bounds__(128) k_wide_v(const uint4 *__restrict__ plo, const uint4 *__restrict__ phi,
-                                                uint8_t *__restrict__ blur, const uint2 *__restrict__ tabg, int w, int h,
+                                                uint8_t *__restrict__ blur, const uint4 *__restrict__ tabg, int w, int h,
                                                 int Sv, int NGa, int wpr, int T, const uint32_t *__restrict__ maskbits) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int NGt = 4 + Sv - 1;
-    uint4 *sA = reinterpret_cast<uint4 *>(wsm);                              // [plane][NGt][half][32 cols]
-    uint2 *tab = reinterpret_cast<uint2 *>(wsm + (size_t)2 * NGt * 2 * WV_COLS * 16);
-    unsigned char *outb = reinterpret_cast<unsigned char *>(tab + (4 * Sv + 3) * 32);      // [4 warps][32 rows][32 cols]
+    const int per = NGt * 2 * WV_COLS;                                        // 16-byte chunks per plane and stage
+    uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][32 slots]
+    uint4 *tab = sB + 4 * per;                                                // [2 Sv][32]
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-    const int f = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, X0 = blockIdx.x * WV_COLS, G0 = Y0 >> 5;
-    for (int i = tid; i < (4 * Sv + 3) * 32; i += 128) tab[i] = __ldg(tabg + i);
-    {
-        const int per = NGt * 2 * WV_COLS;            // chunks per plane
+    const int f = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, XS = blockIdx.x * (WV_COLS * WV_NT), G0 = Y0 >> 5;
+    for (int i = tid; i < 2 * Sv * 32; i += 128) tab[i] = __ldg(tabg + i);
+    const int nt = min(WV_NT, (w - XS + WV_COLS - 1) / WV_COLS);
+    auto issue = [&](int ct) {
+        const int X0 = XS + ct * WV_COLS;
+        const uint32_t dst0 = wsmem_u32(sB + (ct & 1) * 2 * per);
         for (int i = tid; i < 2 * per; i += 128) {
             const int pl = i >= per, j = pl ? i - per : i;
             const int col = j & (WV_COLS - 1), gh = j >> 5;          // gh = 2 * group + half
             const int G = G0 + (gh >> 1);
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (X0 + col < w && G < NGa) v = __ldg((pl ? phi : plo) + (((size_t)f * NGa + G) * 2 + (gh & 1)) * w + X0 + col);
-            sA[i] = v;
+            const bool ok = X0 + col < w && G < NGa;
+            const uint4 *srcp = (pl ? phi : plo) + (((size_t)f * NGa + (ok ? G : 0)) * 2 + (gh & 1)) * w + (ok ? X0 + col : 0);
+            wcp_async16(dst0 + (pl * per + gh * WV_COLS + wv_slot(col)) * 16, srcp, ok);
         }
-    }
-    __syncthreads();
-    int acc[2][2][4][4];       // [plane][column tile][row block][4]
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    const int g = lane >> 2, t = lane & 3;
+    // ldmatrix rows of a pair of column blocks (nb = 2 np, 2 np + 1): matrices (nb0, half 0), (nb0, half 1), (nb1, half 0), (nb1, half 1)
+    uint32_t boff[2];
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+    for (int np = 0; np < 2; np++) {
+        const int mi = lane >> 3, n = lane & 7;
+        const int nb = 2 * np + (mi >> 1), half = mi & 1;
+        const int col = 8 * (n >> 1) + 2 * nb + (n & 1);
+        boff[np] = (half * WV_COLS + wv_slot(col)) * 16;
+    }
+    for (int ct = 0; ct < nt; ct++) {
+        if (ct + 1 < nt) {
+            issue(ct + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int X0 = XS + ct * WV_COLS;
+        int acc[2][2][4][4];       // [plane][row tile][column block][4]; the low plane starts at the rounding constant
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
             for (int c2 = 0; c2 < 4; c2++)
 #pragma unroll
-                for (int d = 0; d < 4; d++) acc[a][b][c2][d] = 0;
-    // ldmatrix rows: matrices (cols 0-7, half 0), (cols 8-15, half 0), (cols 0-7, half 1), (cols 8-15, half 1)
-    const uint32_t abase = wsmem_u32(sA) + (((lane >> 4) * WV_COLS) + (lane & 7) + 8 * ((lane >> 3) & 1)) * 16;
-    const uint32_t plane_stride = NGt * 2 * WV_COLS * 16;
-    for (int s = 0; s < Sv; s++) {
-        uint32_t a[2][2][4];
-#pragma unroll
-        for (int pl = 0; pl < 2; pl++)
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-                wldsm_x4(abase + pl * plane_stride + (wq + s) * (2 * WV_COLS * 16) + mt * 256, a[pl][mt]);
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-            const uint2 b = tab[(4 * s - nb + 3) * 32 + lane];
+                for (int d = 0; d < 4; d++) { acc[0][b][c2][d] = 32768; acc[1][b][c2][d] = 0; }
+        const uint32_t sbase = wsmem_u32(sB + (ct & 1) * 2 * per);
+        for (int s = 0; s < Sv; s++) {
+            uint32_t bq[2][2][4];        // [plane][block pair][4]
 #pragma unroll
             for (int pl = 0; pl < 2; pl++)
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) wimma(acc[pl][mt][nb], a[pl][mt], b);
-        }
-    }
-    // epilogue: thread (g, t) holds columns 16 mt + g (+8), output rows 8 nb + 2t (+1) of the warp's 32 x 32 block
-    const int g = lane >> 2, t = lane & 3;
-    unsigned char *ob = outb + wq * 1024;
+                for (int np = 0; np < 2; np++)
+                    wldsm_x4(sbase + (pl * per + (wq + s) * 2 * WV_COLS) * 16 + boff[np], bq[pl][np]);
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++)
+            for (int mt = 0; mt < 2; mt++) {
+                const uint4 a = tab[(2 * s - mt + 1) * 32 + lane];
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++)
+                for (int pl = 0; pl < 2; pl++)
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int v = ((acc[1][mt][nb][d] << 8) + acc[0][mt][nb][d] + 32768) >> 16;
-                ob[(8 * nb + 2 * t + (d & 1)) * 32 + 16 * mt + g + 8 * (d >> 1)] = (unsigned char)v;
+                    for (int nb = 0; nb < 4; nb++)
+                        wimma(acc[pl][mt][nb], a.x, a.y, a.z, a.w, bq[pl][nb >> 1][2 * (nb & 1)], bq[pl][nb >> 1][2 * (nb & 1) + 1]);
             }
-    __syncwarp();
-    const int y = Y0 + 32 * wq + lane;
-    if (y < h) {
+        }
+        // epilogue: thread (g, t) holds output rows 16 mt + g (+8), columns 8 t + 2 nb + e
         const int sidx = f / T;
-        const uint32_t m = maskbits[((size_t)sidx * h + y) * wpr + (X0 >> 5)];
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(ob + lane * 32);
-        uint8_t *dst = blur + ((size_t)f * h + y) * w + X0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (X0 + 4 * i < w) {
-                const uint32_t mk = (m >> (4 * i)) & 0xFu;
-                const uint32_t zero = (((mk * 0x00204081u) & 0x01010101u) * 0xFFu);       // masked pixels -> 0xFF bytes
-                *reinterpret_cast<uint32_t *>(dst + 4 * i) = src[i] & ~zero;
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++) {
+                const int y = Y0 + 32 * wq + 16 * mt + g + 8 * hr;
+                uint32_t wd[2];
+#pragma unroll
+                for (int wi = 0; wi < 2; wi++) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int nb = 2 * wi + (q >> 1), d = 2 * hr + (q & 1);
+                        v[q] = (uint32_t)(acc[1][mt][nb][d] * 256 + acc[0][mt][nb][d]);      // blur = byte 2
+                    }
+                    wd[wi] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+                }
+                if (y < h) {
+                    const uint32_t m = (__ldg(maskbits + ((size_t)sidx * h + y) * wpr + (X0 >> 5)) >> (8 * t)) & 0xFFu;
+                    uint8_t *dst = blur + ((size_t)f * h + y) * w + X0 + 8 * t;
+#pragma unroll
+                    for (int wi = 0; wi < 2; wi++)
+                        if (X0 + 8 * t + 4 * wi < w) {
+                            const uint32_t mk = (m >> (4 * wi)) & 0xFu;
+                            const uint32_t zero = ((mk * 0x00204081u) & 0x01010101u) * 0xFFu;     // masked pixels -> 0xFF bytes
+                            *reinterpret_cast<uint32_t *>(dst + 4 * wi) = wd[wi] & ~zero;
+                        }
+                }
             }
-        }
+        __syncthreads();       // every warp is done with this stage before the loads of tile ct + 2 overwrite it
     }
 }
 
-int fm_launch_wide_blur(fm_ctx *c, int T, cudaStream_t st) {
+// identity-resize gray plane (parity tap of the fused conversion), defined in k_frontend.cu
+int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
+
+// frames != nullptr: full-resolution mode, convert BGR -> gray while staging (no gray plane); else read c->gray
+int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
     const WideGeom g = wide_geom(c);
     const int F = c->S * T;
     uint32_t *plo = reinterpret_cast<uint32_t *>(c->hor);
     uint32_t *phi = plo + fm_wide_plane_bytes(c) / 4;
-    const uint2 *tabh = c->wtab, *tabv = c->wtab + (size_t)(4 * g.Sh + 3) * 32;
+    const uint2 *tabh = reinterpret_cast<const uint2 *>(c->wtab);
+    const uint4 *tabv = reinterpret_cast<const uint4 *>(c->wtab + (size_t)(4 * g.Sh + 3) * 32 * 2);
     const size_t smh = (size_t)32 * g.pitch + (size_t)(4 * g.Sh + 3) * 256;
-    const size_t smv = (size_t)2 * (4 + g.Sv - 1) * 2 * WV_COLS * 16 + (size_t)(4 * g.Sv + 3) * 256 + 4 * 1024;
+    const size_t smv = (size_t)4 * (4 + g.Sv - 1) * 2 * WV_COLS * 16 + (size_t)2 * g.Sv * 512;
     if (smh > 200 * 1024 || smv > 200 * 1024) {
         fm_set_error("Gaussian kernel %d too wide for the tensor-core blur (%zu / %zu bytes of shared memory)", c->k, smh, smv);
         return FM_ERANGE;
     }
     static size_t conf_h[FM_MAX_DEVICES] = {0}, conf_v[FM_MAX_DEVICES] = {0};
     size_t &ch = conf_h[c->cfg.device % FM_MAX_DEVICES], &cv = conf_v[c->cfg.device % FM_MAX_DEVICES];
-    if (smh > ch) { FM_CUDA(cudaFuncSetAttribute(k_wide_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh)); ch = smh; }
+    if (smh > ch) {
+        FM_CUDA(cudaFuncSetAttribute(k_wide_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
+        FM_CUDA(cudaFuncSetAttribute(k_wide_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
+        ch = smh;
+    }
     if (smv > cv) { FM_CUDA(cudaFuncSetAttribute(k_wide_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv)); cv = smv; }
     dim3 hgrid((c->w + WH_COLS - 1) / WH_COLS, g.NGa, F);
-    k_wide_h<<<hgrid, 128, smh, st>>>(c->gray, plo, phi, tabh, c->w, c->h, g.r, g.R16, g.Sh, g.pitch, g.NGa);
+    const bool aligned4 = frames && ((((uintptr_t)frames) | sstride | fstride) & 3) == 0;
+    if (aligned4) {
+        if (c->cfg.flags & FM_FLAG_KEEP_PLANES) {
+            int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
+            if (rc) return rc;
+        }
+        k_wide_h<true><<<hgrid, WH_THREADS, smh, st>>>(frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
+                                                       g.Sh, g.pitch, g.NGa);
+    } else {
+        if (frames) {
+            int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
+            if (rc) return rc;
+        }
+        k_wide_h<false><<<hgrid, WH_THREADS, smh, st>>>(c->gray, 0, 0, T, plo, phi, tabh, c->w, c->h, g.r, g.R16, g.Sh,
+                                                        g.pitch, g.NGa);
+    }
     FM_LAUNCH_CHECK();
-    dim3 vgrid((c->w + WV_COLS - 1) / WV_COLS, (c->h + WV_ROWS - 1) / WV_ROWS, F);
+    dim3 vgrid((c->w + WV_COLS * WV_NT - 1) / (WV_COLS * WV_NT), (c->h + WV_ROWS - 1) / WV_ROWS, F);
     k_wide_v<<<vgrid, 128, smv, st>>>(reinterpret_cast<const uint4 *>(plo), reinterpret_cast<const uint4 *>(phi), c->blur,
                                       tabv, c->w, c->h, g.Sv, g.NGa, c->wpr, T, c->maskbits);
     FM_LAUNCH_CHECK();
