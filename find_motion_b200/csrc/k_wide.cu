@@ -19,6 +19,8 @@
 //   (ldmatrix.x4 = two column blocks).  The columns of a block are permuted (block nb holds columns
 //   8t' + 2nb + e) so that a thread ends up with 8 consecutive output bytes of a row: mask, two 32-bit stores.
 //   The planes stream through a cp.async double buffer along a strip of column tiles.
+#include <type_traits>
+
 #include "fm_common.cuh"
 
 #define WH_COLS 256        // pass 1 CTA tile: 32 padded rows (one group) x 256 columns, 8 warps of 32 x 32
@@ -37,6 +39,13 @@ __device__ __forceinline__ void wimma(int (&d)[4], uint32_t a0, uint32_t a1, uin
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// first step of a chain: D = A * B + c (the same constant in all four lanes)
+__device__ __forceinline__ void wimma0(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1, int c) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c));
 }
 __device__ __forceinline__ void wcp_async16(uint32_t dst, const void *src, bool valid) {
     const int n = valid ? 16 : 0;                 // src-size 0: the 16 bytes are zero-filled
@@ -124,7 +133,7 @@ __device__ __forceinline__ uint32_t wgray4(uint32_t w0, uint32_t w1, uint32_t w2
 }
 
 // grid: (ceil(w / 256), NGa, F), 256 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
-// BGR: src = the caller's frames (identity resize, 4-byte aligned rows); otherwise src = the gray plane [F][h][w].
+// BGR: src = the caller's frames (identity resize, 16-byte aligned rows); otherwise src = the gray plane [F][h][w].
 template <bool BGR>
 __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
                                                        uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
@@ -137,31 +146,56 @@ __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict
     const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
     for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
     // stage the window: shared column cc <-> image column X0 - R16 + cc (reflected), row rr <-> padded row 32 G + rr
-    {
+    if (BGR) {
+        // warp wq: rows wq, wq+8, wq+16, wq+24; lane: a unit of 16 pixels = 48 BGR bytes (three 128-bit loads); the
+        // loads of the four rows are issued before the first conversion
+        const uint8_t *fr = src + (size_t)(f / T) * sstride + (size_t)(f % T) * fstride;
+        const uint8_t *rp[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) rp[i] = fr + (size_t)fm_reflect101(32 * G + wq + 8 * i - r, h) * w * 3;
+        const int upr = pitch >> 4;
+        for (int u = lane; u < upr; u += 32) {
+            const int x = X0 - R16 + 16 * u;
+            if (x >= 0 && x + 15 < w) {
+                uint4 raw[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(rp[i] + 3 * x);
+                    raw[i][0] = __ldg(q); raw[i][1] = __ldg(q + 1); raw[i][2] = __ldg(q + 2);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint4 o;
+                    o.x = wgray4(raw[i][0].x, raw[i][0].y, raw[i][0].z);
+                    o.y = wgray4(raw[i][0].w, raw[i][1].x, raw[i][1].y);
+                    o.z = wgray4(raw[i][1].z, raw[i][1].w, raw[i][2].x);
+                    o.w = wgray4(raw[i][2].y, raw[i][2].z, raw[i][2].w);
+                    *reinterpret_cast<uint4 *>(tile + (wq + 8 * i) * pitch + 16 * u) = o;
+                }
+            } else {
+#pragma unroll 1
+                for (int b = 0; b < 16; b++) {
+                    const int xx = 3 * fm_reflect101(x + b, w);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tile[(wq + 8 * i) * pitch + 16 * u + b] = (unsigned char)wgray1(rp[i] + xx);
+                }
+            }
+        }
+    } else {
         const int words = pitch >> 2;
-        const uint8_t *fr = BGR ? src + (size_t)(f / T) * sstride + (size_t)(f % T) * fstride : src + (size_t)f * h * w;
-        const int px = BGR ? 3 : 1;
+        const uint8_t *fr = src + (size_t)f * h * w;
 #pragma unroll 1
         for (int rr = wq; rr < 32; rr += WH_THREADS / 32) {
-            const uint8_t *row = fr + (size_t)fm_reflect101(32 * G + rr - r, h) * w * px;
+            const uint8_t *row = fr + (size_t)fm_reflect101(32 * G + rr - r, h) * w;
             uint32_t *trow = reinterpret_cast<uint32_t *>(tile + rr * pitch);
             for (int cw = lane; cw < words; cw += 32) {
                 const int x = X0 - R16 + 4 * cw;
                 uint32_t v;
-                if (x >= 0 && x + 3 < w) {
-                    if (BGR) {
-                        const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 3 * x);
-                        v = wgray4(__ldg(q), __ldg(q + 1), __ldg(q + 2));
-                    } else {
-                        v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-                    }
-                } else {
+                if (x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+                else {
                     v = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int xx = fm_reflect101(x + b, w);
-                        v |= (BGR ? wgray1(row + 3 * xx) : (uint32_t)row[xx]) << (8 * b);
-                    }
+                    for (int b = 0; b < 4; b++) v |= (uint32_t)row[fm_reflect101(x + b, w)] << (8 * b);
                 }
                 trow[cw] = v;
             }
@@ -189,18 +223,18 @@ __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict
     }
     // thread (g, t): rows g, g+8 (tile 0), g+16, g+24 (tile 1) of columns 2t, 2t+1 of each block = word g of the group
     const int g = lane >> 2, t = lane & 3;
-    const size_t gbase = (((size_t)f * NGa + G) * 2 + (g >> 2)) * w;
+    const int xb = X0 + 32 * wq + 2 * t;
+    const size_t o0 = ((((size_t)f * NGa + G) * 2 + (g >> 2)) * w + xb) * 4 + (g & 3);
+    uint32_t *ql = plo + o0, *qh = phi + o0;
 #pragma unroll
     for (int nb = 0; nb < 4; nb++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int x = X0 + 32 * wq + 8 * nb + 2 * t + e;
-            if (x < w) {
+            if (xb + 8 * nb + e < w) {
                 const uint32_t p = __byte_perm(acc[0][nb][e], acc[0][nb][2 + e], 0x5140);     // [r0.b0, r8.b0, r0.b1, r8.b1]
                 const uint32_t q = __byte_perm(acc[1][nb][e], acc[1][nb][2 + e], 0x5140);
-                const size_t o = (gbase + x) * 4 + (g & 3);
-                plo[o] = __byte_perm(p, q, 0x5410);
-                phi[o] = __byte_perm(p, q, 0x7632);
+                ql[(8 * nb + e) * 4] = __byte_perm(p, q, 0x5410);
+                qh[(8 * nb + e) * 4] = __byte_perm(p, q, 0x7632);
             }
         }
 }
@@ -210,7 +244,7 @@ __device__ __forceinline__ int wv_slot(int c) { return (c & 24) | ((c & 7) ^ (((
 
 // grid: (ceil(w / (32 WV_NT)), ceil(h / 128), F), 128 threads.
 // dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 32 columns * 16 B  +  2 Sv * 512
-__global__ void __launch_bounds__(128) k_wide_v(const uint4 *__restrict__ plo, const uint4 *__restrict__ phi,
+__global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo, const uint4 *__restrict__ phi,
                                                 uint8_t *__restrict__ blur, const uint4 *__restrict__ tabg, int w, int h,
                                                 int Sv, int NGa, int wpr, int T, const uint32_t *__restrict__ maskbits) {
     extern __shared__ __align__(16) unsigned char wsm[];
@@ -222,16 +256,18 @@ __global__ void __launch_bounds__(128) k_wide_v(const uint4 *__restrict__ plo, c
     const int f = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, XS = blockIdx.x * (WV_COLS * WV_NT), G0 = Y0 >> 5;
     for (int i = tid; i < 2 * Sv * 32; i += 128) tab[i] = __ldg(tabg + i);
     const int nt = min(WV_NT, (w - XS + WV_COLS - 1) / WV_COLS);
+    // staging: lane = column of the tile, warp = chunk row q (plane, group, half) modulo 4
+    const uint4 *gsrc = plo + ((size_t)f * NGa + G0) * 2 * w + XS + lane;
+    const size_t pdiff = phi - plo;
+    const uint32_t sdst = wsmem_u32(sB) + wv_slot(lane) * 16;
     auto issue = [&](int ct) {
         const int X0 = XS + ct * WV_COLS;
-        const uint32_t dst0 = wsmem_u32(sB + (ct & 1) * 2 * per);
-        for (int i = tid; i < 2 * per; i += 128) {
-            const int pl = i >= per, j = pl ? i - per : i;
-            const int col = j & (WV_COLS - 1), gh = j >> 5;          // gh = 2 * group + half
-            const int G = G0 + (gh >> 1);
-            const bool ok = X0 + col < w && G < NGa;
-            const uint4 *srcp = (pl ? phi : plo) + (((size_t)f * NGa + (ok ? G : 0)) * 2 + (gh & 1)) * w + (ok ? X0 + col : 0);
-            wcp_async16(dst0 + (pl * per + gh * WV_COLS + wv_slot(col)) * 16, srcp, ok);
+        const bool okx = X0 + lane < w;
+        for (int q = wq; q < 4 * NGt; q += 4) {
+            const int pl = q >= 2 * NGt, gh = q - pl * 2 * NGt;          // gh = 2 * group + half
+            const bool ok = okx && G0 + (gh >> 1) < NGa;
+            const uint4 *srcp = gsrc + (ok ? (size_t)gh * w + ct * WV_COLS + (pl ? pdiff : 0) : 0);
+            wcp_async16(sdst + (((ct & 1) * 2 + pl) * per + gh * WV_COLS) * 16, srcp, ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -256,14 +292,8 @@ __global__ void __launch_bounds__(128) k_wide_v(const uint4 *__restrict__ plo, c
         __syncthreads();
         const int X0 = XS + ct * WV_COLS;
         int acc[2][2][4][4];       // [plane][row tile][column block][4]; the low plane starts at the rounding constant
-#pragma unroll
-        for (int b = 0; b < 2; b++)
-#pragma unroll
-            for (int c2 = 0; c2 < 4; c2++)
-#pragma unroll
-                for (int d = 0; d < 4; d++) { acc[0][b][c2][d] = 32768; acc[1][b][c2][d] = 0; }
         const uint32_t sbase = wsmem_u32(sB + (ct & 1) * 2 * per);
-        for (int s = 0; s < Sv; s++) {
+        auto step = [&](int s, auto first) {
             uint32_t bq[2][2][4];        // [plane][block pair][4]
 #pragma unroll
             for (int pl = 0; pl < 2; pl++)
@@ -276,10 +306,16 @@ __global__ void __launch_bounds__(128) k_wide_v(const uint4 *__restrict__ plo, c
 #pragma unroll
                 for (int pl = 0; pl < 2; pl++)
 #pragma unroll
-                    for (int nb = 0; nb < 4; nb++)
-                        wimma(acc[pl][mt][nb], a.x, a.y, a.z, a.w, bq[pl][nb >> 1][2 * (nb & 1)], bq[pl][nb >> 1][2 * (nb & 1) + 1]);
+                    for (int nb = 0; nb < 4; nb++) {
+                        const uint32_t b0 = bq[pl][nb >> 1][2 * (nb & 1)], b1 = bq[pl][nb >> 1][2 * (nb & 1) + 1];
+                        if (decltype(first)::value) wimma0(acc[pl][mt][nb], a.x, a.y, a.z, a.w, b0, b1, pl ? 0 : 32768);
+                        else wimma(acc[pl][mt][nb], a.x, a.y, a.z, a.w, b0, b1);
+                    }
             }
-        }
+        };
+        step(0, std::true_type());
+#pragma unroll 1
+        for (int s = 1; s < Sv; s++) step(s, std::false_type());
         // epilogue: thread (g, t) holds output rows 16 mt + g (+8), columns 8 t + 2 nb + e
         const int sidx = f / T;
 #pragma unroll
@@ -340,8 +376,8 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
     }
     if (smv > cv) { FM_CUDA(cudaFuncSetAttribute(k_wide_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv)); cv = smv; }
     dim3 hgrid((c->w + WH_COLS - 1) / WH_COLS, g.NGa, F);
-    const bool aligned4 = frames && ((((uintptr_t)frames) | sstride | fstride) & 3) == 0;
-    if (aligned4) {
+    const bool aligned16 = frames && ((((uintptr_t)frames) | sstride | fstride | ((size_t)c->w * 3)) & 15) == 0;
+    if (aligned16) {
         if (c->cfg.flags & FM_FLAG_KEEP_PLANES) {
             int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
             if (rc) return rc;
