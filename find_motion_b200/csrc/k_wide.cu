@@ -118,6 +118,14 @@ int fm_wide_init(fm_ctx *c, const int *taps) {
     return FM_OK;
 }
 
+// source row of padded row index i (BORDER_REFLECT_101).  One reflection is enough when the plane is taller than
+// the kernel radius; rows past the padded range (their taps are all zero) only have to stay inside the plane.
+__device__ __forceinline__ int wrow(int i, int n) {
+    if (i >= 0 && i < n) return i;
+    const int j = i < 0 ? -i : 2 * n - 2 - i;
+    return (j >= 0 && j < n) ? j : fm_reflect101(i, n);
+}
+
 __device__ __forceinline__ uint32_t wgray1(const uint8_t *p) {
     return (3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15;
 }
@@ -135,7 +143,7 @@ __device__ __forceinline__ uint32_t wgray4(uint32_t w0, uint32_t w1, uint32_t w2
 // grid: (ceil(w / 256), NGa, F), 256 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
 // BGR: src = the caller's frames (identity resize, 16-byte aligned rows); otherwise src = the gray plane [F][h][w].
 template <bool BGR>
-__global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
+__global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
                                                        uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
                                                        const uint2 *__restrict__ tabg, int w, int h, int r, int R16, int Sh,
                                                        int pitch, int NGa) {
@@ -152,10 +160,13 @@ __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict
         const uint8_t *fr = src + (size_t)(f / T) * sstride + (size_t)(f % T) * fstride;
         const uint8_t *rp[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) rp[i] = fr + (size_t)fm_reflect101(32 * G + wq + 8 * i - r, h) * w * 3;
+        for (int i = 0; i < 4; i++) rp[i] = fr + (size_t)wrow(32 * G + wq + 8 * i - r, h) * (w * 3);
         const int upr = pitch >> 4;
+        const int xneed = min(X0 + WH_COLS, w) + r;           // first column no output of this CTA reads
+        const bool mirror = R16 < w && R16 + r < WH_COLS;      // border columns are copies of staged columns (one reflection)
         for (int u = lane; u < upr; u += 32) {
             const int x = X0 - R16 + 16 * u;
+            if (x >= xneed) continue;
             if (x >= 0 && x + 15 < w) {
                 uint4 raw[4][3];
 #pragma unroll
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict
                     o.w = wgray4(raw[i][2].y, raw[i][2].z, raw[i][2].w);
                     *reinterpret_cast<uint4 *>(tile + (wq + 8 * i) * pitch + 16 * u) = o;
                 }
-            } else {
+            } else if (!mirror) {
 #pragma unroll 1
                 for (int b = 0; b < 16; b++) {
                     const int xx = 3 * fm_reflect101(x + b, w);
@@ -181,46 +192,62 @@ __global__ void __launch_bounds__(WH_THREADS) k_wide_h(const uint8_t *__restrict
                 }
             }
         }
+        if (mirror && (X0 == 0 || X0 + WH_COLS + r > w)) {       // BORDER_REFLECT_101 columns from their mirror images
+            __syncthreads();
+            const int nl = X0 == 0 ? R16 : 0;                    // shared columns [0, nl) are x < 0
+            const int c0 = w - X0 + R16;                         // shared column of x = w
+            const int nr = X0 + WH_COLS + r > w ? r : 0;
+            for (int i = tid; i < 32 * (nl + nr); i += WH_THREADS) {
+                const int rr = i / (nl + nr), j = i - rr * (nl + nr);
+                const int c = j < nl ? j : c0 + (j - nl);
+                const int cm = j < nl ? 2 * R16 - c : 2 * (c0 - 1) - c;      // x -> -x, x -> 2w - 2 - x
+                tile[rr * pitch + c] = tile[rr * pitch + cm];
+            }
+        }
     } else {
         const int words = pitch >> 2;
         const uint8_t *fr = src + (size_t)f * h * w;
 #pragma unroll 1
         for (int rr = wq; rr < 32; rr += WH_THREADS / 32) {
-            const uint8_t *row = fr + (size_t)fm_reflect101(32 * G + rr - r, h) * w;
+            const uint8_t *row = fr + (size_t)wrow(32 * G + rr - r, h) * w;
             uint32_t *trow = reinterpret_cast<uint32_t *>(tile + rr * pitch);
             for (int cw = lane; cw < words; cw += 32) {
                 const int x = X0 - R16 + 4 * cw;
+                if (x >= min(X0 + WH_COLS, w) + r) break;
                 uint32_t v;
                 if (x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
                 else {
                     v = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) v |= (uint32_t)row[fm_reflect101(x + b, w)] << (8 * b);
+                    for (int b = 0; b < 4; b++) v |= (uint32_t)row[wrow(x + b, w)] << (8 * b);
                 }
                 trow[cw] = v;
             }
         }
     }
     __syncthreads();
+    if (X0 + 32 * wq >= w) return;                            // this warp's 32 columns are outside the image
     int acc[2][4][4];
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-            for (int d = 0; d < 4; d++) acc[a][b][d] = 0;
     const uint32_t abase = wsmem_u32(tile) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * pitch + 32 * wq + 16 * (lane >> 4);
-    for (int s = 0; s < Sh; s++) {
+    auto step = [&](int s, auto first) {
         uint32_t a0[4], a1[4];
         wldsm_x4(abase + 32 * s, a0);
         wldsm_x4(abase + 32 * s + 16 * pitch, a1);
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             const uint2 b = tab[(4 * s - nb + 3) * 32 + lane];
-            wimma(acc[0][nb], a0[0], a0[1], a0[2], a0[3], b.x, b.y);
-            wimma(acc[1][nb], a1[0], a1[1], a1[2], a1[3], b.x, b.y);
+            if (decltype(first)::value) {
+                wimma0(acc[0][nb], a0[0], a0[1], a0[2], a0[3], b.x, b.y, 0);
+                wimma0(acc[1][nb], a1[0], a1[1], a1[2], a1[3], b.x, b.y, 0);
+            } else {
+                wimma(acc[0][nb], a0[0], a0[1], a0[2], a0[3], b.x, b.y);
+                wimma(acc[1][nb], a1[0], a1[1], a1[2], a1[3], b.x, b.y);
+            }
         }
-    }
+    };
+    step(0, std::true_type());
+#pragma unroll 1
+    for (int s = 1; s < Sh; s++) step(s, std::false_type());
     // thread (g, t): rows g, g+8 (tile 0), g+16, g+24 (tile 1) of columns 2t, 2t+1 of each block = word g of the group
     const int g = lane >> 2, t = lane & 3;
     const int xb = X0 + 32 * wq + 2 * t;
@@ -256,18 +283,22 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
     const int f = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, XS = blockIdx.x * (WV_COLS * WV_NT), G0 = Y0 >> 5;
     for (int i = tid; i < 2 * Sv * 32; i += 128) tab[i] = __ldg(tabg + i);
     const int nt = min(WV_NT, (w - XS + WV_COLS - 1) / WV_COLS);
-    // staging: lane = column of the tile, warp = chunk row q (plane, group, half) modulo 4
-    const uint4 *gsrc = plo + ((size_t)f * NGa + G0) * 2 * w + XS + lane;
+    // staging: lane = column of the tile, warp = chunk row gh (2 * group + half) modulo 4, both planes
+    const uint4 *gsrc = plo + (((size_t)f * NGa + G0) * 2 + wq) * w + XS + lane;
     const size_t pdiff = phi - plo;
-    const uint32_t sdst = wsmem_u32(sB) + wv_slot(lane) * 16;
+    const uint32_t sdst = wsmem_u32(sB) + (wq * WV_COLS + wv_slot(lane)) * 16;
+    const int ghmax = min(2 * NGt, 2 * (NGa - G0));              // chunk rows that exist in the planes
     auto issue = [&](int ct) {
-        const int X0 = XS + ct * WV_COLS;
-        const bool okx = X0 + lane < w;
-        for (int q = wq; q < 4 * NGt; q += 4) {
-            const int pl = q >= 2 * NGt, gh = q - pl * 2 * NGt;          // gh = 2 * group + half
-            const bool ok = okx && G0 + (gh >> 1) < NGa;
-            const uint4 *srcp = gsrc + (ok ? (size_t)gh * w + ct * WV_COLS + (pl ? pdiff : 0) : 0);
-            wcp_async16(sdst + (((ct & 1) * 2 + pl) * per + gh * WV_COLS) * 16, srcp, ok);
+        const bool okx = XS + ct * WV_COLS + lane < w;
+        const uint4 *sp = gsrc + ct * WV_COLS;
+        uint32_t dp = sdst + (ct & 1) * 2 * per * 16;
+#pragma unroll 1
+        for (int gh = wq; gh < 2 * NGt; gh += 4) {
+            const bool ok = okx && gh < ghmax;
+            wcp_async16(dp, ok ? sp : plo, ok);
+            wcp_async16(dp + per * 16, ok ? sp + pdiff : plo, ok);
+            sp += 4 * (size_t)w;
+            dp += 4 * WV_COLS * 16;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -317,12 +348,15 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
 #pragma unroll 1
         for (int s = 1; s < Sv; s++) step(s, std::false_type());
         // epilogue: thread (g, t) holds output rows 16 mt + g (+8), columns 8 t + 2 nb + e
-        const int sidx = f / T;
+        const int yb = Y0 + 32 * wq + g;
+        const uint32_t *mp = maskbits + ((size_t)(f / T) * h + yb) * wpr + (X0 >> 5);
+        uint8_t *dp0 = blur + ((size_t)f * h + yb) * w + X0 + 8 * t;
+        const bool ok0 = X0 + 8 * t < w, ok1 = X0 + 8 * t + 4 < w;
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
             for (int hr = 0; hr < 2; hr++) {
-                const int y = Y0 + 32 * wq + 16 * mt + g + 8 * hr;
+                const int dy = 16 * mt + 8 * hr;
                 uint32_t wd[2];
 #pragma unroll
                 for (int wi = 0; wi < 2; wi++) {
@@ -334,16 +368,12 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
                     }
                     wd[wi] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
                 }
-                if (y < h) {
-                    const uint32_t m = (__ldg(maskbits + ((size_t)sidx * h + y) * wpr + (X0 >> 5)) >> (8 * t)) & 0xFFu;
-                    uint8_t *dst = blur + ((size_t)f * h + y) * w + X0 + 8 * t;
-#pragma unroll
-                    for (int wi = 0; wi < 2; wi++)
-                        if (X0 + 8 * t + 4 * wi < w) {
-                            const uint32_t mk = (m >> (4 * wi)) & 0xFu;
-                            const uint32_t zero = ((mk * 0x00204081u) & 0x01010101u) * 0xFFu;     // masked pixels -> 0xFF bytes
-                            *reinterpret_cast<uint32_t *>(dst + 4 * wi) = wd[wi] & ~zero;
-                        }
+                if (yb + dy < h) {
+                    const uint32_t m = __ldg(mp + dy * wpr) >> (8 * t);
+                    uint8_t *dst = dp0 + dy * w;
+                    // masked pixels -> 0xFF bytes -> cleared
+                    if (ok0) *reinterpret_cast<uint32_t *>(dst) = wd[0] & ~((((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                    if (ok1) *reinterpret_cast<uint32_t *>(dst + 4) = wd[1] & ~(((((m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
                 }
             }
         __syncthreads();       // every warp is done with this stage before the loads of tile ct + 2 overwrite it
