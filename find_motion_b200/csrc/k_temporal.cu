@@ -22,13 +22,43 @@ __device__ __forceinline__ uint32_t fm_bg8(double bg) {
     return __float_as_uint(__fadd_rn(f, 12582912.0f)) & 0x1FFu;
 }
 
-template <bool TAIL>
-__device__ __forceinline__ double fm_bg_update(double bg, uint32_t src, double alpha, double beta) {
-    double s = fm_u8_to_f64(src);
-    if (!TAIL) return __fma_rn(bg, beta, __dmul_rn(s, alpha));
-    return __fma_rn(s, alpha, __dmul_rn(bg, beta));
+// One frame of one lane: 16 pixels (bytes of px[4]) -> 16 threshold bits (bit j = pixel j), background updated.
+// TAIL: the lane holds the N mod 16 remainder group (A.6: the product order of the AVX2 tail);
+// SAFE: alpha in [0, 1] and threshold >= 0, so bg stays in [0, 255] (no fabs / saturation) and
+//       rn(blur * alpha) = fma(2^52 + blur, alpha, -(2^52 * alpha)) exactly (no int -> double conversion);
+// INIT: first frame of the stream (ref_frame = blur.astype(float)).
+template <bool TAIL, bool SAFE, bool INIT>
+__device__ __forceinline__ uint32_t fm_temporal16(const uint32_t (&px)[4], double (&b)[16], int threshold, double alpha,
+                                                  double beta) {
+    const double nC = -(4503599627370496.0 * alpha);
+    const int qoff = 0x4B400000 - threshold;
+    const uint32_t nthr2 = ~(2u * (uint32_t)threshold);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t src = __byte_perm(px[j >> 2], 0, 0x4440 + (j & 3));
+        if (SAFE && !TAIL) {
+            const double X = __hiloint2double(0x43300000, (int)src);
+            if (INIT) b[j] = X - 4503599627370496.0;
+            const int q = __float_as_int(__fadd_rn(__double2float_rn(b[j]), 12582912.0f));     // 0x4B400000 + bg8
+            // bits = 2 * bits + (|bg8 - blur| > threshold): q - qoff - src in [0, 2 thr] unless above the threshold
+            uint32_t tmp;
+            asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}"
+                : "+r"(bits), "=r"(tmp) : "r"((uint32_t)(q - qoff - (int)src)), "r"(nthr2));
+            b[j] = __fma_rn(b[j], beta, __fma_rn(X, alpha, nC));
+        } else {
+            const double sd = fm_u8_to_f64(src);
+            if (INIT) b[j] = sd;
+            int d = (int)src - (int)fm_bg8(b[j]);
+            d = d < 0 ? -d : d;
+            bits = 2u * bits + (d > threshold ? 1u : 0u);
+            b[j] = TAIL ? __fma_rn(sd, alpha, __dmul_rn(b[j], beta)) : __fma_rn(b[j], beta, __dmul_rn(sd, alpha));
+        }
+    }
+    return __brev(bits) >> 16;          // pixel 0 was pushed first
 }
 
+template <bool SAFE>
 __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ blur, double *__restrict__ bg,
                                                   uint32_t *__restrict__ tflat, const StreamState *__restrict__ state,
                                                   int T, int N, int ntiles, int threshold, double alpha,
@@ -67,16 +97,11 @@ __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ bl
             for (int j = 0; j < nvalid; j++) px[j >> 2] |= (uint32_t)bl[j] << (8 * (j & 3));
         }
         bl += N;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            uint32_t src = (px[j >> 2] >> (8 * (j & 3))) & 255u;
-            if (t == 0 && !has_bg) b[j] = fm_u8_to_f64(src);      // ref_frame = blur.astype(float)
-            int d = (int)src - (int)fm_bg8(b[j]);
-            d = d < 0 ? -d : d;
-            bits |= (d > threshold ? 1u : 0u) << j;
-            b[j] = tail ? fm_bg_update<true>(b[j], src, alpha, beta) : fm_bg_update<false>(b[j], src, alpha, beta);
-        }
+        uint32_t bits;
+        if (t == 0 && !has_bg) bits = tail ? fm_temporal16<true, SAFE, true>(px, b, threshold, alpha, beta)
+                                           : fm_temporal16<false, SAFE, true>(px, b, threshold, alpha, beta);
+        else if (tail) bits = fm_temporal16<true, SAFE, false>(px, b, threshold, alpha, beta);
+        else bits = fm_temporal16<false, SAFE, false>(px, b, threshold, alpha, beta);
         if (nvalid < 16) bits &= (1u << nvalid) - 1u;
         uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 1);
         if ((lane & 1) == 0) *tw = bits | (hi << 16);
@@ -105,8 +130,11 @@ int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st) {
     double alpha = c->cfg.avg;
     double beta = 1.0 - alpha;
     dim3 grid((c->ntiles + 7) / 8, c->S);
-    k_temporal<<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
-                                     alpha, beta, c->rawrange, c->w, c->h);
+    const bool safe = alpha >= 0.0 && alpha <= 1.0 && c->cfg.threshold >= 0;
+    if (safe) k_temporal<true><<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
+                                                     alpha, beta, c->rawrange, c->w, c->h);
+    else k_temporal<false><<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
+                                                 alpha, beta, c->rawrange, c->w, c->h);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
