@@ -65,7 +65,7 @@ struct fm_ctx {
     uint32_t *tflat;           // [S][Tmax][ntiles*16]  raw threshold, flat bit order
     uint32_t *dil;             // [S][Tmax][h][wpr]  dilated threshold, row-padded bit plane
     uint32_t *fill;            // [S][Tmax][h][wpr]  dilated threshold with holes filled
-    int *any;                  // [S][Tmax][2] row range of set pixels: (max y, max h-1-y), -1 = none
+    int *any;                  // [S][Tmax][4] range of set pixels: (max y, max h-1-y, max word column j, max wpr-1-j), -1 = none
     int *rawrange;             // [S][Tmax][2] row range of the RAW threshold (written by the temporal kernels)
     int *heavy;                // [S][Tmax] frame needs the global-memory labelling kernel
     int *ncomp;                // [S][Tmax]

@@ -267,7 +267,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->tflat, (F * flatw + FM_TILE_WORDS) * 4);
     ALLOC(c->dil, F * c->h * c->wpr * 4);
     ALLOC(c->fill, F * c->h * c->wpr * 4);
-    ALLOC(c->any, F * 2 * sizeof(int));      // per frame: row range of the dilated mask
+    ALLOC(c->any, F * 4 * sizeof(int));      // per frame: row and word-column range of the dilated mask
     ALLOC(c->ncomp, F * sizeof(int));
     ALLOC(c->heavy, F * sizeof(int));
     ALLOC(c->rawrange, F * 2 * sizeof(int));

@@ -38,7 +38,43 @@ __device__ __forceinline__ uint32_t flat_row_word(const uint32_t *flat, int y, i
     return v;
 }
 
-// rowrange[2f] = max y with a set pixel (-1: none), rowrange[2f+1] = max (h-1-y)  (memset 0xFF before)
+// one row of the 5x5 dilation (two iterations of the 3x3 default kernel, out-of-image pixels ignored): lanes hold the
+// words of the row; returns the OR of the lane's words and the lane's first / last non-empty word column
+template <bool ALIGNED>
+__device__ __forceinline__ uint32_t dilate_row(const uint32_t *__restrict__ flat, uint32_t *__restrict__ out, int y, int w,
+                                               int h, int wpr, int lane, int &jmin, int &jmax) {
+    uint32_t anyw = 0;
+    for (int j = lane; j < wpr; j += 32) {
+        uint32_t vm = 0, vc = 0, vp = 0;    // vertical OR of words j-1, j, j+1
+#pragma unroll
+        for (int dy = -2; dy <= 2; dy++) {
+            int yy = y + dy;
+            if (ALIGNED) {                  // w % 32 == 0: flat order == row-padded order
+                if ((unsigned)yy < (unsigned)h) {
+                    const uint32_t *r = flat + (size_t)yy * wpr;
+                    vc |= __ldcg(r + j);
+                    if (j > 0) vm |= __ldcg(r + j - 1);
+                    if (j + 1 < wpr) vp |= __ldcg(r + j + 1);
+                }
+            } else {
+                vm |= flat_row_word(flat, yy, j - 1, w, h, wpr);
+                vc |= flat_row_word(flat, yy, j, w, h, wpr);
+                vp |= flat_row_word(flat, yy, j + 1, w, h, wpr);
+            }
+        }
+        uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) |
+                     (vp << 30);
+        int rem = w - 32 * j;
+        if (rem < 32) d &= (1u << rem) - 1u;
+        out[j] = d;
+        anyw |= d;
+        if (d) { jmax = j; jmin = min(jmin, j); }
+    }
+    return anyw;
+}
+
+// rowrange[4f] = max y with a set pixel (-1: none), [4f+1] = max (h-1-y), [4f+2] = max word column j with a set
+// pixel, [4f+3] = max (wpr-1-j)   (memset 0xFF before)
 template <bool ALIGNED>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t *__restrict__ tflat,
                                                                  uint32_t *__restrict__ dil, int *__restrict__ rowrange,
@@ -56,35 +92,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t 
     }
     const uint32_t *flat = tflat + (size_t)f * flatwords;
     uint32_t *out = dil + ((size_t)f * h + y) * wpr;
-    uint32_t anyw = 0;
-    for (int j = lane; j < wpr; j += 32) {
-        uint32_t vm = 0, vc = 0, vp = 0;    // vertical OR of words j-1, j, j+1
-#pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            int yy = y + dy;
-            if (ALIGNED) {                  // w % 32 == 0: flat order == row-padded order
-                if ((unsigned)yy < (unsigned)h) {
-                    const uint32_t *r = flat + (size_t)yy * wpr;
-                    vc |= __ldg(r + j);
-                    if (j > 0) vm |= __ldg(r + j - 1);
-                    if (j + 1 < wpr) vp |= __ldg(r + j + 1);
-                }
-            } else {
-                vm |= flat_row_word(flat, yy, j - 1, w, h, wpr);
-                vc |= flat_row_word(flat, yy, j, w, h, wpr);
-                vp |= flat_row_word(flat, yy, j + 1, w, h, wpr);
-            }
+    int jmax = -1, jmin = wpr;
+    const uint32_t anyw = dilate_row<ALIGNED>(flat, out, y, w, h, wpr, lane, jmin, jmax);
+    if (__any_sync(0xffffffffu, anyw != 0)) {
+        jmax = __reduce_max_sync(0xffffffffu, jmax);
+        jmin = __reduce_min_sync(0xffffffffu, jmin);
+        if (lane == 0) {
+            atomicMax(rowrange + 4 * f, y);
+            atomicMax(rowrange + 4 * f + 1, h - 1 - y);
+            atomicMax(rowrange + 4 * f + 2, jmax);
+            atomicMax(rowrange + 4 * f + 3, wpr - 1 - jmin);
         }
-        uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) |
-                     (vp << 30);
-        int rem = w - 32 * j;
-        if (rem < 32) d &= (1u << rem) - 1u;
-        out[j] = d;
-        anyw |= d;
-    }
-    if (__any_sync(0xffffffffu, anyw != 0) && lane == 0) {
-        atomicMax(rowrange + 2 * f, y);
-        atomicMax(rowrange + 2 * f + 1, h - 1 - y);
     }
 }
 
@@ -94,7 +112,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_dilate(const uint32_t 
 struct CclArgs {
     const uint32_t *plane;     // [F][h][wpr] dilated bit plane
     uint32_t *fill;            // [F][h][wpr] dilated plane with holes filled (written by the kernel)
-    const int *rowrange;       // [F][2] from k_dilate (NULL: label every row of every frame)
+    const int *rowrange;       // [F][4] from k_dilate (NULL: label every row and column of every frame)
+    const uint32_t *raw;       // [F][flatwords] raw threshold bits: the shared-memory kernel dilates them into `plane`
+    const int *rawrange;       //   itself (rows of [F][2] rawrange +- 3) and writes the ranges to `rangeout`;
+    int *rangeout;             //   NULL: `plane` is already dilated
+    uint32_t *planeout;
+    int flatwords, aligned;
     int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
     int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
     int w, h, wpr, cap;
@@ -329,7 +352,7 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
     int ylo = 0, yhi = a.h - 1;
     if (a.rowrange) {
-        int ymax = a.rowrange[2 * f], ymin = a.h - 1 - a.rowrange[2 * f + 1];
+        int ymax = a.rowrange[4 * f], ymin = a.h - 1 - a.rowrange[4 * f + 1];
         if (ymax < 0) return;                       // no set pixel in this frame
         ylo = max(ymin - 1, 0);
         yhi = min(ymax + 1, a.h - 1);
@@ -482,18 +505,16 @@ __device__ __forceinline__ void srow_union(const RunTable &t, int id0, int yr, i
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
-    extern __shared__ __align__(16) unsigned char csm[];
-    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
+// One frame.  The labelling runs on the window of word columns [jlo, jlo + wprw) that holds every set pixel (from
+// k_dilate): background that touches a window edge is connected to the outside of the image exactly as background
+// that touches the image border is (there is no foreground beyond the window to enclose it), so the result is
+// identical, and a 1080p / 4K frame whose motion spans <= 1024 columns runs with one word per lane (KW = 1).
+template <int KW>
+__device__ __forceinline__ void ccl_frame_window(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
+                                                 int ylo, int yhi, int jlo, int wprw) {
+    constexpr int K = KW;
+    const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int ylo = 0, yhi = a.h - 1;
-    if (a.rowrange) {
-        int ymax = a.rowrange[2 * f], ymin = a.h - 1 - a.rowrange[2 * f + 1];
-        if (ymax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
-        ylo = max(ymin - 1, 0);
-        yhi = min(ymax + 1, a.h - 1);
-    }
     const int nrows = yhi - ylo + 1;
     RunTable bg, fg;
     bg.row = reinterpret_cast<int2 *>(csm);
@@ -509,15 +530,15 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
     __shared__ int cur_bg, cur_fg, overflow;
     if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
     __syncthreads();
-    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr;
-    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr;
+    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
+    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
 
     // ---- pass 1: background runs (4-connected, linked to the outside) ----
     for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {          // two rows in flight per warp
         uint32_t B0[K], B1[K], S[K], E[K];
         const int yr1 = yr + CCL2_WARPS;
-        row_words<K, true>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, B0);
-        if (yr1 < nrows) row_words<K, true>(dil + (size_t)(ylo + yr1) * a.wpr, a.w, a.wpr, lane, B1);
+        row_words<K, true>(dil + (size_t)(ylo + yr) * a.wpr, ww, wprw, lane, B0);
+        if (yr1 < nrows) row_words<K, true>(dil + (size_t)(ylo + yr1) * a.wpr, ww, wprw, lane, B1);
         row_starts_ends<K>(B0, lane, S, E);
         if (!row_append<K>(S, E, lane, yr, 1, bg, &cur_bg)) overflow = 1;
         if (yr1 < nrows) {
@@ -527,12 +548,12 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(bg, 1, yr, ylo + yr, a.w, a.h, lane);
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(bg, 1, yr, ylo + yr, ww, a.h, lane);
     __syncthreads();
     // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
     for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
         uint32_t F[K], S[K], E[K];
-        row_words<K, false>(dil + (size_t)(ylo + yr) * a.wpr, a.w, a.wpr, lane, F);
+        row_words<K, false>(dil + (size_t)(ylo + yr) * a.wpr, ww, wprw, lane, F);
         const int2 r = bg.row[yr];
         for (int b = 0; b < r.y; b += 32) {
             const int i = b + lane;
@@ -554,7 +575,7 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         }
 #pragma unroll
         for (int k = 0; k < K; k++)
-            if (lane + 32 * k < a.wpr) fil[(size_t)(ylo + yr) * a.wpr + lane + 32 * k] = F[k];
+            if (lane + 32 * k < wprw) fil[(size_t)(ylo + yr) * a.wpr + lane + 32 * k] = F[k];
         row_starts_ends<K>(F, lane, S, E);
         if (!row_append<K>(S, E, lane, yr, 0, fg, &cur_fg)) overflow = 1;
     }
@@ -569,7 +590,7 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
     }
     // ---- pass 2: filled foreground, 8-connected ----
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(fg, 0, yr, ylo + yr, a.w, a.h, lane);
+    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(fg, 0, yr, ylo + yr, ww, a.h, lane);
     __syncthreads();
     // ---- per-run bit-quad area and bounding box -> root ----
     // The 2x2-window masks of a row pair are computed word-parallel (lanes hold the words of rows y-1 and y),
@@ -581,8 +602,8 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
         if (has_up) {
             uint32_t L[K], U[K];
-            row_words<K, false>(fil + (size_t)y * a.wpr, a.w, a.wpr, lane, L);
-            row_words<K, false>(fil + (size_t)(y - 1) * a.wpr, a.w, a.wpr, lane, U);
+            row_words<K, false>(fil + (size_t)y * a.wpr, ww, wprw, lane, L);
+            row_words<K, false>(fil + (size_t)(y - 1) * a.wpr, ww, wprw, lane, U);
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 uint32_t ln = __shfl_down_sync(0xffffffffu, L[k], 1), un = __shfl_down_sync(0xffffffffu, U[k], 1);
@@ -627,10 +648,60 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         if (!skipped) atomicAdd(a.ncounted + f, 1);
         if (slot < a.maxc) {
             fm_component c;
-            c.area_x2 = ar; c.x = bb.x; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
+            c.area_x2 = ar; c.x = bb.x + 32 * jlo; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
             a.comps[(size_t)f * a.maxc + slot] = c;
         }
     }
+}
+
+template <int K>
+__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
+    int ylo = 0, yhi = a.h - 1, jlo = 0, jhi = a.wpr - 1;
+    if (a.raw) {
+        // ---- 5x5 dilation of the raw threshold bits of this frame (rows within 3 of a pixel above threshold) ----
+        const int rmax = a.rawrange[2 * f], rmin = a.h - 1 - a.rawrange[2 * f + 1];
+        if (rmax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }      // quiet frame: rangeout stays (-1, ...)
+        __shared__ int rng[4];
+        if (threadIdx.x < 4) rng[threadIdx.x] = -1;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t *flat = a.raw + (size_t)f * a.flatwords;
+        uint32_t *dplane = a.planeout + (size_t)f * a.h * a.wpr;
+        int jmax = -1, jmin = a.wpr, ymx = -1, ymn = a.h;
+        for (int y = max(rmin - 3, 0) + warp; y <= min(rmax + 3, a.h - 1); y += CCL2_WARPS) {
+            const uint32_t anyw = a.aligned ? dilate_row<true>(flat, dplane + (size_t)y * a.wpr, y, a.w, a.h, a.wpr, lane, jmin, jmax)
+                                            : dilate_row<false>(flat, dplane + (size_t)y * a.wpr, y, a.w, a.h, a.wpr, lane, jmin, jmax);
+            if (__any_sync(0xffffffffu, anyw != 0)) { ymx = y; ymn = min(ymn, y); }
+        }
+        jmax = __reduce_max_sync(0xffffffffu, jmax);
+        jmin = __reduce_min_sync(0xffffffffu, jmin);
+        if (lane == 0 && ymx >= 0) {
+            atomicMax(&rng[0], ymx);
+            atomicMax(&rng[1], a.h - 1 - ymn);
+            atomicMax(&rng[2], jmax);
+            atomicMax(&rng[3], a.wpr - 1 - jmin);
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) a.rangeout[4 * f + threadIdx.x] = rng[threadIdx.x];
+        if (rng[0] < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
+        ylo = max(a.h - 1 - rng[1] - 1, 0);
+        yhi = min(rng[0] + 1, a.h - 1);
+        jhi = rng[2];
+        jlo = a.wpr - 1 - rng[3];
+    } else if (a.rowrange) {
+        int ymax = a.rowrange[4 * f], ymin = a.h - 1 - a.rowrange[4 * f + 1];
+        if (ymax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
+        ylo = max(ymin - 1, 0);
+        yhi = min(ymax + 1, a.h - 1);
+        jhi = a.rowrange[4 * f + 2];
+        jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
+    }
+    const int wprw = jhi - jlo + 1;
+    if (K > 1 && wprw <= 32) ccl_frame_window<1>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    else if (K > 2 && wprw <= 64) ccl_frame_window<2>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    else ccl_frame_window<K>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -701,7 +772,7 @@ __global__ void k_u8_to_bits(const uint8_t *__restrict__ src, uint32_t *__restri
 int fm_launch_thresh_export(fm_ctx *c, int stream, int t, uint8_t *dst_dev, cudaStream_t st) {
     const uint32_t *pl = c->dil + ((size_t)stream * c->last_T + t) * c->h * c->wpr;
     dim3 grid((c->w + 127) / 128, c->h);
-    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 255, c->any + 2 * ((size_t)stream * c->last_T + t));
+    k_bits_to_u8<<<grid, 128, 0, st>>>(pl, dst_dev, c->w, c->h, c->wpr, 255, c->any + 4 * ((size_t)stream * c->last_T + t));
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -738,13 +809,16 @@ void fm_ccl_free(CclScratch *s) {
 }
 
 // labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
-static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, const int *rowrange, int F, int w,
+static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
-                   int max_area, int *errflag, int *heavy, int T, int t0, int Th, cudaStream_t st) {
+                   int max_area, int *errflag, int *heavy, int T, int t0, int Th, cudaStream_t st,
+                   const uint32_t *raw = nullptr, const int *rawrange = nullptr, int flatwords = 0) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
         CclArgs a;
         a.plane = plane; a.fill = fill; a.rowrange = rowrange;
+        a.raw = raw; a.rawrange = rawrange; a.rangeout = rowrange; a.planeout = const_cast<uint32_t *>(plane);
+        a.flatwords = flatwords; a.aligned = (w % 32) == 0;
         a.T = T; a.t0 = t0; a.Th = Th;
         a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
@@ -773,6 +847,7 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
         } else {
+            a.raw = nullptr;
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, nullptr);
             FM_LAUNCH_CHECK();
         }
@@ -783,7 +858,7 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
 // clears the per-frame result slots of a call (row ranges, counts); once per call, before any range
 int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st) {
     const int F = c->S * T;
-    FM_CUDA(cudaMemsetAsync(c->any, 0xFF, (size_t)F * 2 * sizeof(int), st));     // row ranges: (-1, -1)
+    FM_CUDA(cudaMemsetAsync(c->any, 0xFF, (size_t)F * 4 * sizeof(int), st));     // row / column ranges: -1
     FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (size_t)F * sizeof(int), st));
     FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
     return FM_OK;
@@ -792,6 +867,12 @@ int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st) {
 // dilation + contours of frames [t0, t0+Th) of every stream of a T-frame call
 int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st) {
     const int F = c->S * Th;
+    // With enough frames to fill the GPU (one CTA per frame) the shared-memory labelling kernel dilates the raw
+    // threshold bits of its frame itself; with few frames the grid-wide k_dilate (one warp per row) is faster.
+    if (c->wpr <= 128 && F >= 64)
+        return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
+                       c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st, c->tflat,
+                       c->rawrange, c->ntiles * FM_TILE_WORDS);
     int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (c->w % 32 == 0)
         k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
