@@ -654,6 +654,211 @@ __device__ __forceinline__ void ccl_frame_window(const CclArgs &a, int *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow windows: G = 8 or 16 lanes per row, 32 / G rows per warp.  The motion of a frame usually spans a few
+// hundred columns, i.e. <= 8 or 16 words; with one row per warp 3/4 or 1/2 of the lanes would idle through every
+// shuffle, scan and table walk.  Same algorithm as ccl_frame_window: lane sl = lane % G holds word sl of the
+// window row of its group; neighbour shuffles stop at the group boundary; scans and broadcasts use the
+// shuffle width G.  Full-mask collectives only (every lane executes every collective; inactive groups carry zeros).
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void g_starts_ends(uint32_t B, int sl, uint32_t &S, uint32_t &E) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, B, 1), dn = __shfl_down_sync(0xffffffffu, B, 1);
+    const uint32_t Bp = sl ? up : 0u, Bn = sl < G - 1 ? dn : 0u;
+    S = B & ~((B << 1) | (Bp >> 31));
+    E = B & ~((B >> 1) | (Bn << 31));
+}
+
+template <int G>
+__device__ __forceinline__ bool g_append(uint32_t S, uint32_t E, int sl, bool act, int yr, int id0, const RunTable &t,
+                                         int *cursor) {
+    const int cs = __popc(S), ce = __popc(E);
+    int p = cs | (ce << 16);                    // starts and ends scanned together (a row holds < 65536 runs)
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, p, o, G);
+        if (sl >= o) p += v;
+    }
+    const int n = __shfl_sync(0xffffffffu, p, G - 1, G) & 0xffff;      // runs of the row
+    int off = 0;
+    if (sl == 0 && act) {
+        off = n ? atomicAdd(cursor, n) : 0;
+        t.row[yr] = make_int2(off, n);
+    }
+    off = __shfl_sync(0xffffffffu, off, 0, G);
+    if (n == 0) return true;
+    if (off + n > CCL2_CAP) return false;
+    int is = off + (p & 0xffff) - cs, ie = off + (p >> 16) - ce;
+    const int x0 = 32 * sl;
+    while (S) {
+        const int bit = __ffs(S) - 1;
+        S &= S - 1;
+        t.xs[is] = (uint16_t)(x0 + bit);
+        t.parent[id0 + is] = id0 + is;
+        is++;
+    }
+    while (E) {
+        const int bit = __ffs(E) - 1;
+        E &= E - 1;
+        t.xe[ie] = (uint16_t)(x0 + bit);
+        ie++;
+    }
+    return true;
+}
+
+template <bool CONN8, bool OUTSIDE, int G>
+__device__ __forceinline__ void g_union(const RunTable &t, int id0, int yr, int y, int w, int h, int sl) {
+    const int2 cur = t.row[yr];
+    if (cur.y == 0) return;
+    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
+    const int d = CONN8 ? 1 : 0;
+    for (int i = sl; i < cur.y; i += G) {
+        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
+        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(t.parent, id, 0);
+        if (prv.y) {
+            int lo = 0, hi = prv.y;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)t.xe[prv.x + mid] < xs - d) lo = mid + 1; else hi = mid;
+            }
+            for (int q = lo; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) suf_union(t.parent, id, id0 + prv.x + q);
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void ccl_frame_window_g(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
+                                                   int ylo, int yhi, int jlo, int wprw) {
+    constexpr int R = 32 / G;                                  // rows per warp
+    const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane & (G - 1), gi = lane / G;
+    const int nrows = yhi - ylo + 1;
+    RunTable bg, fg;
+    bg.row = reinterpret_cast<int2 *>(csm);
+    fg.row = bg.row + a.h;
+    bg.parent = reinterpret_cast<int *>(fg.row + a.h);
+    fg.parent = bg.parent + CCL2_CAP + 2;
+    bg.xs = reinterpret_cast<uint16_t *>(fg.parent + CCL2_CAP + 2);
+    bg.xe = bg.xs + CCL2_CAP;
+    fg.xs = bg.xe + CCL2_CAP;
+    fg.xe = fg.xs + CCL2_CAP;
+    uint32_t *q4s = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP) + warp * 64;
+    uint32_t *q3s = q4s + 32;
+    __shared__ int cur_bg, cur_fg, overflow;
+    if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
+    __syncthreads();
+    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
+    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
+
+    // ---- pass 1: background runs (4-connected, linked to the outside) ----
+    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
+        const int yr = base + gi;
+        const bool act = yr < nrows;
+        const uint32_t B = act ? plane_word<true>(dil + (size_t)(ylo + yr) * a.wpr, sl, ww, wprw) : 0u;
+        uint32_t S, E;
+        g_starts_ends<G>(B, sl, S, E);
+        if (!g_append<G>(S, E, sl, act, yr, 1, bg, &cur_bg)) overflow = 1;
+    }
+    __syncthreads();
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R)
+        if (base + gi < nrows) g_union<false, true, G>(bg, 1, base + gi, ylo + base + gi, ww, a.h, sl);
+    __syncthreads();
+    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
+    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
+        const int yr = base + gi;
+        const bool act = yr < nrows;
+        uint32_t F = act ? plane_word<false>(dil + (size_t)(ylo + yr) * a.wpr, sl, ww, wprw) : 0u;
+        const int2 r = act ? bg.row[yr] : make_int2(0, 0);
+        const int rmax = __reduce_max_sync(0xffffffffu, r.y);
+        for (int b = 0; b < rmax; b += G) {
+            const int i = b + sl;
+            bool hole = false;
+            int xs = 0, xe = 0;
+            if (i < r.y) { hole = suf_find(bg.parent, 1 + r.x + i) != 0; xs = bg.xs[r.x + i]; xe = bg.xe[r.x + i]; }
+            uint32_t hm = (__ballot_sync(0xffffffffu, hole) >> (gi * G)) & ((1u << G) - 1u);    // holes of this group
+            const int cmax = __reduce_max_sync(0xffffffffu, __popc(hm));
+            for (int q = 0; q < cmax; q++) {
+                const bool has = hm != 0;
+                const int src = has ? __ffs(hm) - 1 : 0;
+                hm &= hm - 1;
+                const int hxs = __shfl_sync(0xffffffffu, xs, src, G), hxe = __shfl_sync(0xffffffffu, xe, src, G);
+                const int lo = max(hxs - 32 * sl, 0), hi = min(hxe - 32 * sl, 31);
+                if (has && lo <= hi) F |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            }
+        }
+        if (act && sl < wprw) fil[(size_t)(ylo + yr) * a.wpr + sl] = F;
+        uint32_t S, E;
+        g_starts_ends<G>(F, sl, S, E);
+        if (!g_append<G>(S, E, sl, act, yr, 0, fg, &cur_fg)) overflow = 1;
+    }
+    __syncthreads();
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    if (threadIdx.x == 0) heavy[f] = 0;
+    const int total = cur_fg;
+    int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        area2[i] = 0;
+        reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
+    }
+    // ---- pass 2: filled foreground, 8-connected ----
+    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R)
+        if (base + gi < nrows) g_union<true, false, G>(fg, 0, base + gi, ylo + base + gi, ww, a.h, sl);
+    __syncthreads();
+    // ---- per-run bit-quad area and bounding box -> root ----
+    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
+        const int yr = base + gi, y = ylo + yr;
+        const bool act = yr < nrows;
+        const int2 r = act ? fg.row[yr] : make_int2(0, 0);
+        const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
+        const bool ld = act && r.y && has_up;
+        const uint32_t L = ld ? plane_word<false>(fil + (size_t)y * a.wpr, sl, ww, wprw) : 0u;
+        const uint32_t U = ld ? plane_word<false>(fil + (size_t)(y - 1) * a.wpr, sl, ww, wprw) : 0u;
+        uint32_t ln = __shfl_down_sync(0xffffffffu, L, 1), un = __shfl_down_sync(0xffffffffu, U, 1);
+        if (sl == G - 1) { ln = 0; un = 0; }
+        const uint32_t l1 = (L >> 1) | (ln << 31), u1 = (U >> 1) | (un << 31);
+        q4s[lane] = L & l1 & U & u1;
+        q3s[lane] = (L & l1 & (U ^ u1)) | (U & u1 & (L ^ l1));
+        __syncwarp();
+        for (int i = sl; i < r.y; i += G) {
+            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
+            const int root = suf_find(fg.parent, r.x + i);
+            int q = 0;
+            if (has_up) {
+                const int x0 = max(xs - 1, 0), x1 = xe;         // windows owned by this run
+                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
+                    int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
+                    uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    q += 2 * __popc(q4s[gi * G + j] & m) + __popc(q3s[gi * G + j] & m);
+                }
+            }
+            if (q) atomicAdd(area2 + root, q);
+            int *bb = bbox + (size_t)root * 4;
+            atomicMin(bb + 0, xs);
+            atomicMin(bb + 1, y);
+            atomicMax(bb + 2, xe);
+            atomicMax(bb + 3, y);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- roots -> component records ----
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        if (fg.parent[i] != i) continue;
+        const int ar = __ldcg(area2 + i);
+        const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
+        const int slot = atomicAdd(a.ncomp + f, 1);
+        const bool skipped = (2LL * a.max_area < ar) && (ar < 2LL * a.min_area);   // find_motion.py:684
+        if (!skipped) atomicAdd(a.ncounted + f, 1);
+        if (slot < a.maxc) {
+            fm_component c;
+            c.area_x2 = ar; c.x = bb.x + 32 * jlo; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
+            a.comps[(size_t)f * a.maxc + slot] = c;
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
@@ -699,7 +904,9 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
     }
     const int wprw = jhi - jlo + 1;
-    if (K > 1 && wprw <= 32) ccl_frame_window<1>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    if (wprw <= 8) ccl_frame_window_g<8>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    else if (wprw <= 16) ccl_frame_window_g<16>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    else if (K > 1 && wprw <= 32) ccl_frame_window<1>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (K > 2 && wprw <= 64) ccl_frame_window<2>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else ccl_frame_window<K>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
 }

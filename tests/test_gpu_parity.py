@@ -71,6 +71,23 @@ def test_contours_random_planes():
         assert label_components(t) == R.external_components(t), (trial, h, w)
 
 
+def test_contours_random_planes_all_lane_groupings():
+    """Widths that select 8, 16 and 32 lanes per row in the labelling kernel (<= 256, <= 512, wider)."""
+    from find_motion_b200.engine import label_components
+    from oracle import restated as R
+    rng = np.random.default_rng(17)
+    for trial in range(60):
+        w = int(rng.integers(*[(150, 257), (257, 513), (513, 1100)][trial % 3]))
+        h = int(rng.integers(2, 70))
+        dens = rng.choice([0.01, 0.05, 0.2, 0.5, 0.8])
+        t = (rng.random((h, w)) < dens).astype(np.uint8) * 255
+        if rng.random() < 0.6:
+            t = R.dilate5(t)
+        if rng.random() < 0.5:
+            t[rng.random((h, w)) < 0.03] = 0
+        assert label_components(t) == R.external_components(t), (trial, h, w)
+
+
 def test_contours_structured_planes():
     """Nested rings, spirals and border-touching shapes (RETR_EXTERNAL nesting / hole filling)."""
     from find_motion_b200.engine import label_components
