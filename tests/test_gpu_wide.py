@@ -1,0 +1,71 @@
+"""GPU parity of the tensor-core wide Gaussian (k_wide.cu): kernel radii below / at / above the plane size,
+16-byte-aligned BGR staging and the gray-plane staging, border tiles, partial column tiles, row-group padding,
+and the resize front end feeding it.  Everything compared for exact equality with the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(W, H, n, T, kw, seed, n_streams=1, expect_front_end=None):
+    import torch
+    from find_motion_b200 import synth
+    from find_motion_b200.engine import MotionEngine
+    from oracle import restated as R
+    clips = np.stack([synth.make_clip(W, H, n, seed=seed + s, fps=kw.get("fps", 30)) for s in range(n_streams)])
+    orcs = [R.StreamOracle(W, H, **kw) for _ in range(n_streams)]
+    dev = torch.from_numpy(clips).cuda()
+    with MotionEngine(W, H, n_streams=n_streams, max_frames=T, keep_planes=True, **kw) as eng:
+        if expect_front_end is not None:
+            assert eng.info["front_end"] == expect_front_end
+        for t0 in range(0, n, T):
+            t1 = min(n, t0 + T)
+            stats = eng.process(dev[:, t0:t1])
+            for s in range(n_streams):
+                for t in range(t0, t1):
+                    rec = orcs[s].process(clips[s, t], keep_planes=True)
+                    pl = eng.planes(s, t - t0, bg=(t == t1 - 1))
+                    for key in ("gray", "blur", "thresh"):
+                        assert (pl[key] == rec["planes"][key]).all(), \
+                            (key, s, t, np.argwhere(pl[key] != rec["planes"][key])[:4])
+                    if t == t1 - 1:
+                        assert (pl["bg"] == rec["planes"]["bg"]).all(), ("bg", s, t)
+                    _, comps = eng.components(s, t - t0)
+                    assert sorted(a / 2.0 for a, _ in comps) == rec["areas"], (s, t)
+                    st = stats[s, t - t0]
+                    assert (bool(st["movement"]), int(st["movement_counter"]), bool(st["wrote"])) == \
+                        (rec["movement"], rec["counter"], rec["wrote"])
+
+
+# (W, H, blur_scale) -> k = odd(int(W / blur_scale)); full-resolution mode (box_size = W)
+GEOMETRIES = [
+    (320, 240, 20),     # k = 17, 16-byte aligned BGR rows: gray fused into the staging
+    (272, 33, 8),       # k = 35, one and a bit row groups, partial 256-column tile
+    (256, 30, 3),       # k = 85: radius 42 > rows 30 (multiple reflections of rows)
+    (64, 64, 1),        # k = 65: radius 32, mirror condition R16 < w holds narrowly
+    (32, 48, 1),        # k = 33: radius 16 = w / 2, one column tile, slow border path
+    (528, 20, 4),       # k = 133: radius 66 > rows 20, three column tiles
+    (100, 75, 4),       # k = 25, rows not 16-byte aligned: gray plane + per-word staging
+    (36, 28, 3),        # k = 13, tiny plane, w % 16 != 0
+    (1040, 24, 10),     # k = 105, five 256-column tiles with a 16-pixel tail
+]
+
+
+@pytest.mark.parametrize("W,H,bs", GEOMETRIES)
+def test_wide_blur_geometries(W, H, bs):
+    kw = dict(fps=6, box_size=W, blur_scale=bs, threshold=5, avg=0.2, min_time=0.3, cache_time=0.6,
+              mask_areas=[((2, 1), (W // 3, H // 2)), ((W // 2, 0), (W - 1, H // 3), (W // 2, H - 1))])
+    _run(W, H, 9, 4, kw, seed=500 + W, expect_front_end=1)
+
+
+def test_wide_blur_two_streams_mixed_masks():
+    from find_motion_b200 import synth
+    kw = dict(fps=10, box_size=640, blur_scale=20, threshold=8, avg=0.1, min_time=0.2, cache_time=0.4,
+              mask_areas=synth.README_MASKS)                  # k = 33
+    _run(640, 360, 10, 5, kw, seed=610, n_streams=2, expect_front_end=1)
+
+
+def test_wide_blur_after_resize():
+    """Downscaled processing plane (resize front end) with a kernel the fused path does not take: k = 7."""
+    kw = dict(fps=8, box_size=160, blur_scale=22, threshold=6, avg=0.15, min_time=0.3, cache_time=0.5)
+    _run(640, 480, 10, 5, kw, seed=620, expect_front_end=2)
