@@ -47,6 +47,7 @@ struct fm_ctx {
     int ntiles;                // ceil(N / FM_TILE_PX)
     int resize_mode;           // 0 identity, 1 general tables, 2 integer ratio
     bool fused;                // K1 fused stencil+background kernel drives the front end
+    bool wide_fused;           // wide Gaussian: the vertical pass runs the temporal stage too (k_wide_vt)
     int fx, fy;                // integer ratios (mode 2)
     int maxc;
     // tables
@@ -135,6 +136,9 @@ int fm_launch_mask_export(fm_ctx *c, int stream, uint8_t *dst_dev, cudaStream_t 
 bool fm_fused_supported(const fm_ctx *c);
 size_t fm_wide_plane_bytes(const fm_ctx *c);
 int fm_wide_init(fm_ctx *c, const int *taps);
+bool fm_wide_fused_supported(const fm_ctx *c);
+size_t fm_wide_bg_doubles(const fm_ctx *c);
+int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);

@@ -236,6 +236,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
         }
     }
     c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);
+    c->wide_fused = !c->fused && fm_wide_fused_supported(c);
     inf.front_end = c->fused ? 0 : (c->resize_mode == 0 ? 1 : 2);
     {
         std::vector<int> taps = gauss_coeffs(c->k);
@@ -260,7 +261,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->gray, need_planes ? F * c->N : 16);
     ALLOC(c->hor, !need_hor ? 16 : std::max(F * c->N * sizeof(uint16_t), 2 * fm_wide_plane_bytes(c)));
     ALLOC(c->blur, need_planes ? F * c->N + 64 : 64);
-    const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX, c->fused ? fm_fused_bg_doubles(c) : (size_t)0);
+    const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX,
+                                       c->fused ? fm_fused_bg_doubles(c) : (c->wide_fused ? fm_wide_bg_doubles(c) : (size_t)0));
     ALLOC(c->bg, bg_doubles * sizeof(double));
     ALLOC(c->maskbits, (size_t)c->S * c->h * c->wpr * 4);
     ALLOC(c->maskflat, (size_t)c->S * flatw * 4);
@@ -396,7 +398,7 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     } else {
         if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
         if (ev) FM_CUDA(cudaEventRecord(ev[1], st));
-        if ((rc = fm_launch_temporal(c, n_frames, st))) return rc;
+        if (!c->wide_fused && (rc = fm_launch_temporal(c, n_frames, st))) return rc;
         if (ev) FM_CUDA(cudaEventRecord(ev[2], st));
     }
     if ((rc = fm_launch_morph_ccl(c, n_frames, st, stats_dev))) return rc;
@@ -501,7 +503,8 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
     if (bg) {
         double *d = nullptr;
         FM_CUDA(cudaMalloc(&d, (size_t)c->N * sizeof(double)));
-        int rc = c->fused ? fm_launch_bg_export_fused(c, stream, d, 0) : fm_launch_bg_export(c, stream, d, 0);
+        int rc = c->fused ? fm_launch_bg_export_fused(c, stream, d, 0)
+                          : (c->wide_fused ? fm_launch_bg_export_wide(c, stream, d, 0) : fm_launch_bg_export(c, stream, d, 0));
         if (rc) return rc;
         FM_CUDA(cudaMemcpy(bg, d, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
         cudaFree(d);

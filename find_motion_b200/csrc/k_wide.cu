@@ -380,6 +380,215 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 2 fused with the temporal stage (planes with w % 32 == 0, alpha in [0, 1]): the blur never goes to memory.
+// CTA = 128 output rows x 16 columns of ONE stream, walking the T frames of the call in order; the byte planes of
+// frame t+1 stream in through cp.async while frame t is multiplied; a thread ends up with 4 rows x 4 consecutive
+// pixels whose float64 background stays in registers for all T frames (find_motion.py:246-257, 651-659).
+// Background layout: [S][tilesY][tilesX][warp 4][8][lane 32] double2 (thread-private, coalesced).
+// ---------------------------------------------------------------------------------------------
+#define WT_COLS 16
+
+// shared slot of column c of a 16-column tile: the 8 columns {4t' + 2nb + e} of a block land in 8 different 16-byte lanes
+__device__ __forceinline__ int wt_slot(int c) { return c ^ ((c >> 3) << 1); }
+
+struct WideVtParams {
+    const uint4 *plo, *phi;
+    const uint4 *tabg;
+    double *bg;
+    uint32_t *tbits;            // [S][T][flatwords] raw threshold bits (flat order == row-padded order since w % 32 == 0)
+    const uint32_t *maskbits;   // [S][h][wpr]
+    const StreamState *state;
+    int *rawrange;              // [S][T][2]
+    uint8_t *blur_out;          // [S][T][h][w] parity tap (KEEP) or null
+    int w, h, Sv, NGa, wpr, T, threshold, tilesX, tilesY;
+    size_t flatwords;           // words per frame of tbits
+    double alpha, beta;
+};
+
+// 4 pixels of one row: lo / hi plane sums -> masked blur bytes -> threshold bits (bit j = pixel j), background update
+template <bool INIT>
+__device__ __forceinline__ uint32_t wt_temporal4(const int (&lo)[4], const int (&hi)[4], uint32_t keep, double (&bg)[4],
+                                                 int qoff, uint32_t nthr2, double alpha, double beta, double nC,
+                                                 uint32_t &blur4) {
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = (uint32_t)(hi[j] * 256 + lo[j]);           // blur = byte 2 (rounding constant in lo)
+    // mask_off_areas paints BLACK into blur: keep has 0x00 bytes at the masked pixels
+    blur4 = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410) & keep;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t sv = __byte_perm(blur4, 0, 0x4440 + j);
+        const double X = __hiloint2double(0x43300000, (int)sv);                     // 2^52 + blur
+        if (INIT) bg[j] = X - 4503599627370496.0;
+        const int q = __float_as_int(__fadd_rn(__double2float_rn(bg[j]), 12582912.0f));
+        uint32_t tmp;
+        asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits), "=r"(tmp) : "r"((uint32_t)(q - qoff - (int)sv)), "r"(nthr2));
+        bg[j] = __fma_rn(bg[j], beta, __fma_rn(X, alpha, nC));
+    }
+    return __brev(bits) >> 28;       // bit j = pixel j
+}
+
+// grid: (w / 16, ceil(h / 128), S), 128 threads.
+// dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 16 columns * 16 B  +  2 Sv * 512
+__global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    const int Sv = p.Sv, w = p.w, h = p.h, NGa = p.NGa, T = p.T;
+    const int NGt = 4 + Sv - 1;
+    const int per = NGt * 2 * WT_COLS;                                        // 16-byte chunks per plane and stage
+    uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][16 slots]
+    uint4 *tab = sB + 4 * per;                                                // [2 Sv][32]
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    const int s = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, X0 = blockIdx.x * WT_COLS, G0 = Y0 >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int i = tid; i < 2 * Sv * 32; i += 128) tab[i] = __ldg(p.tabg + i);
+    // staging: 16 lanes = the columns of the tile, 8 chunk rows gh (2 * group + half) per pass of the CTA, both planes
+    const int scol = tid & 15, sgh = tid >> 4;
+    const size_t fstride = (size_t)NGa * 2 * w;                               // uint4 per frame and plane
+    const uint4 *gsrc = p.plo + ((size_t)s * T * NGa + G0) * 2 * w + (size_t)sgh * w + X0 + scol;
+    const size_t pdiff = p.phi - p.plo;
+    const uint32_t sdst = wsmem_u32(sB) + (sgh * WT_COLS + wt_slot(scol)) * 16;
+    const int ghmax = min(2 * NGt, 2 * (NGa - G0));
+    auto issue = [&](int t) {
+        const uint4 *sp = gsrc + (size_t)t * fstride;
+        uint32_t dp = sdst + (t & 1) * 2 * per * 16;
+#pragma unroll 1
+        for (int gh = sgh; gh < 2 * NGt; gh += 8) {
+            const bool ok = gh < ghmax;
+            wcp_async16(dp, ok ? sp : p.plo, ok);
+            wcp_async16(dp + per * 16, ok ? sp + pdiff : p.plo, ok);
+            sp += 8 * (size_t)w;
+            dp += 8 * WT_COLS * 16;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    // ldmatrix rows of the two column blocks: matrices (nb0, half 0), (nb0, half 1), (nb1, half 0), (nb1, half 1)
+    uint32_t boff;
+    {
+        const int mi = lane >> 3, n = lane & 7;
+        const int col = 4 * (n >> 1) + 2 * (mi >> 1) + (n & 1);
+        boff = ((mi & 1) * WT_COLS + wt_slot(col)) * 16;
+    }
+    // this thread's pixels: rows Y0 + 32 wq + 16 mt + 8 hr + g, columns X0 + 4 t4 .. + 3 (pixel j: block j >> 1, e = j & 1)
+    const int yb = Y0 + 32 * wq + g, xb = X0 + 4 * t4;
+    uint32_t keep[4];                                                         // byte masks of the rows: 0x00 = masked pixel
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int y = yb + 16 * (r >> 1) + 8 * (r & 1);
+        const uint32_t m = y < h ? (__ldg(p.maskbits + ((size_t)s * h + y) * p.wpr + (xb >> 5)) >> (xb & 31)) & 0xFu : 0u;
+        keep[r] = ~(((m * 0x00204081u) & 0x01010101u) * 0xFFu);
+    }
+    const bool has_bg = p.state[s].has_bg != 0;
+    double2 *bgt = reinterpret_cast<double2 *>(p.bg) +
+                   ((((size_t)s * p.tilesY + blockIdx.y) * p.tilesX + blockIdx.x) * 4 + wq) * 8 * 32 + lane;
+    double bg[4][4];
+    if (has_bg) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double2 v = bgt[i * 32];
+            bg[i >> 1][2 * (i & 1)] = v.x;
+            bg[i >> 1][2 * (i & 1) + 1] = v.y;
+        }
+    }
+    const int qoff = 0x4B400000 - p.threshold;
+    const uint32_t nthr2 = ~(2u * (uint32_t)p.threshold);
+    const double nC = -(4503599627370496.0 * p.alpha);
+    uint16_t *tw = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * T * p.flatwords) + (size_t)2 * (X0 >> 5) + ((X0 >> 4) & 1);
+    for (int t = 0; t < T; t++) {
+        if (t + 1 < T) {
+            issue(t + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        int acc[2][2][2][4];       // [plane][row tile][column block][4]; the low plane starts at the rounding constant
+        const uint32_t sbase = wsmem_u32(sB + (t & 1) * 2 * per);
+        auto step = [&](int sg, auto first) {
+            uint32_t bq[2][4];
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) wldsm_x4(sbase + (pl * per + (wq + sg) * 2 * WT_COLS) * 16 + boff, bq[pl]);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const uint4 a = tab[(2 * sg - mt + 1) * 32 + lane];
+#pragma unroll
+                for (int pl = 0; pl < 2; pl++)
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++) {
+                        if (decltype(first)::value) wimma0(acc[pl][mt][nb], a.x, a.y, a.z, a.w, bq[pl][2 * nb], bq[pl][2 * nb + 1], pl ? 0 : 32768);
+                        else wimma(acc[pl][mt][nb], a.x, a.y, a.z, a.w, bq[pl][2 * nb], bq[pl][2 * nb + 1]);
+                    }
+            }
+        };
+        step(0, std::true_type());
+#pragma unroll 1
+        for (int sg = 1; sg < Sv; sg++) step(sg, std::false_type());
+        // ---- temporal stage on the thread's 4 rows x 4 pixels ----
+        bool anyb = false;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int mt = r >> 1, hr = r & 1;
+            const int y = yb + 16 * mt + 8 * hr;
+            int lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { lo[j] = acc[0][mt][j >> 1][2 * hr + (j & 1)]; hi[j] = acc[1][mt][j >> 1][2 * hr + (j & 1)]; }
+            uint32_t blur4;
+            uint32_t nib = (t == 0 && !has_bg)
+                               ? wt_temporal4<true>(lo, hi, keep[r], bg[r], qoff, nthr2, p.alpha, p.beta, nC, blur4)
+                               : wt_temporal4<false>(lo, hi, keep[r], bg[r], qoff, nthr2, p.alpha, p.beta, nC, blur4);
+            if (y >= h) nib = 0;
+            // the 4 lanes of a row: 16 pixels -> one 16-bit store
+            uint32_t v = nib << (4 * t4);
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t4 == 0 && y < h) tw[(size_t)y * p.wpr * 2] = (uint16_t)v;
+            anyb |= v != 0;
+            if (p.blur_out && y < h) *reinterpret_cast<uint32_t *>(p.blur_out + (((size_t)s * T + t) * h + y) * w + xb) = blur4;
+        }
+        if (__any_sync(0xffffffffu, anyb) && lane == 0) {       // this warp's 32 rows hold something
+            int *rr = p.rawrange + 2 * ((size_t)s * T + t);
+            atomicMax(rr, min(Y0 + 32 * wq + 31, h - 1));
+            atomicMax(rr + 1, h - 1 - (Y0 + 32 * wq));
+        }
+        tw += p.flatwords * 2;
+        __syncthreads();       // every warp is done with this stage before the loads of frame t + 2 overwrite it
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) bgt[i * 32] = make_double2(bg[i >> 1][2 * (i & 1)], bg[i >> 1][2 * (i & 1) + 1]);
+}
+
+// tiled background of k_wide_vt -> row-major float64 plane
+__global__ void k_bg_export_wide(const double *__restrict__ bg, double *__restrict__ dst, int w, int h, int tilesX, int tilesY,
+                                 int s) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int tx = x / WT_COLS, ty = y / WV_ROWS, lx = x % WT_COLS, ly = y % WV_ROWS;
+    const int wq = ly >> 5, l32 = ly & 31, mt = l32 >> 4, hr = (l32 >> 3) & 1, g = l32 & 7;
+    const int t4 = lx >> 2, j = lx & 3, lane = 4 * g + t4, r = 2 * mt + hr;
+    const int i = 2 * r + (j >> 1);                                // double2 index of the thread
+    const size_t base = ((((size_t)s * tilesY + ty) * tilesX + tx) * 4 + wq) * 8 * 32;
+    dst[(size_t)y * w + x] = bg[(base + (size_t)i * 32 + lane) * 2 + (j & 1)];
+}
+
+bool fm_wide_fused_supported(const fm_ctx *c) {
+    const double a = c->cfg.avg;
+    return c->k >= 3 && (c->w % 32) == 0 && a >= 0.0 && a <= 1.0 && c->cfg.threshold >= 0;
+}
+
+size_t fm_wide_bg_doubles(const fm_ctx *c) {
+    return (size_t)c->S * ((c->w + WT_COLS - 1) / WT_COLS) * ((c->h + WV_ROWS - 1) / WV_ROWS) * WT_COLS * WV_ROWS;
+}
+
+int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st) {
+    dim3 grid((c->w + 127) / 128, c->h);
+    k_bg_export_wide<<<grid, 128, 0, st>>>(c->bg, dst_dev, c->w, c->h, (c->w + WT_COLS - 1) / WT_COLS,
+                                           (c->h + WV_ROWS - 1) / WV_ROWS, stream);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
 // identity-resize gray plane (parity tap of the fused conversion), defined in k_frontend.cu
 int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 
@@ -423,6 +632,24 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
                                                         g.pitch, g.NGa);
     }
     FM_LAUNCH_CHECK();
+    if (c->wide_fused) {
+        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512;
+        static size_t conf_t[FM_MAX_DEVICES] = {0};
+        size_t &ct = conf_t[c->cfg.device % FM_MAX_DEVICES];
+        if (smt > ct) { FM_CUDA(cudaFuncSetAttribute(k_wide_vt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt)); ct = smt; }
+        WideVtParams p;
+        p.plo = reinterpret_cast<const uint4 *>(plo); p.phi = reinterpret_cast<const uint4 *>(phi); p.tabg = tabv;
+        p.bg = c->bg; p.tbits = c->tflat; p.maskbits = c->maskbits; p.state = c->state; p.rawrange = c->rawrange;
+        p.blur_out = (c->cfg.flags & FM_FLAG_KEEP_PLANES) ? c->blur : nullptr;
+        p.w = c->w; p.h = c->h; p.Sv = g.Sv; p.NGa = g.NGa; p.wpr = c->wpr; p.T = T; p.threshold = c->cfg.threshold;
+        p.tilesX = (c->w + WT_COLS - 1) / WT_COLS; p.tilesY = (c->h + WV_ROWS - 1) / WV_ROWS;
+        p.flatwords = (size_t)c->ntiles * FM_TILE_WORDS;
+        p.alpha = c->cfg.avg; p.beta = 1.0 - p.alpha;
+        dim3 tgrid(p.tilesX, p.tilesY, c->S);
+        k_wide_vt<<<tgrid, 128, smt, st>>>(p);
+        FM_LAUNCH_CHECK();
+        return FM_OK;
+    }
     dim3 vgrid((c->w + WV_COLS * WV_NT - 1) / (WV_COLS * WV_NT), (c->h + WV_ROWS - 1) / WV_ROWS, F);
     k_wide_v<<<vgrid, 128, smv, st>>>(reinterpret_cast<const uint4 *>(plo), reinterpret_cast<const uint4 *>(phi), c->blur,
                                       tabv, c->w, c->h, g.Sv, g.NGa, c->wpr, T, c->maskbits);
