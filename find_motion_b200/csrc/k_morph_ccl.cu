@@ -11,6 +11,8 @@
 // Both labellings are run-based union-find with one warp per row: lanes hold the 32-bit words
 // of the row, run starts/ends come from shifted-word logic and are enumerated with warp prefix
 // sums, unions are lock-free atomicMin links between runs of adjacent rows.
+#include <cstdlib>
+
 #include "fm_common.cuh"
 
 #define WARPS_PER_BLOCK 8
@@ -118,6 +120,7 @@ struct CclArgs {
     int *rangeout;             //   NULL: `plane` is already dilated
     uint32_t *planeout;
     int flatwords, aligned;
+    int lanes;                 // row-per-lane labelling (ccl_frame_lanes)
     int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
     int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
     int w, h, wpr, cap;
@@ -859,6 +862,214 @@ __device__ __forceinline__ void ccl_frame_window_g(const CclArgs &a, int *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One ROW PER LANE.  Rows of a motion mask hold a handful of runs, so a warp that spreads one row over its lanes
+// spends ~800 instructions per row on shuffles, scans and table walks with most lanes idle.  Here every lane walks
+// the words of its own row sequentially (run extraction, two-pointer unions with the row above, hole filling,
+// bit-quad statistics), 32 rows per warp in parallel; the only warp collective left is the prefix sum that hands
+// out run-table slots.  Same tables, same union-find, same results.
+// ---------------------------------------------------------------------------------------------
+template <bool INVERT>
+__device__ __forceinline__ uint32_t win_word(const uint32_t *row, int j, int ww, int wprw) {
+    if ((unsigned)j >= (unsigned)wprw) return 0u;
+    uint32_t v = row[j];
+    if (INVERT) {
+        v = ~v;
+        const int rem = ww - 32 * j;
+        if (rem < 32) v &= (1u << rem) - 1u;
+    }
+    return v;
+}
+
+// runs of the lane's row -> run table (count pass, warp scan for the slots, emit pass); false = table full
+template <bool INVERT>
+__device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int yr, int id0, const RunTable &t, int *cursor,
+                                             int ww, int wprw, int lane) {
+    int n = 0;
+    if (act) {
+        uint32_t carry = 0;
+        for (int j = 0; j < wprw; j++) {
+            const uint32_t B = win_word<INVERT>(row, j, ww, wprw);
+            n += __popc(B & ~((B << 1) | carry));
+            carry = B >> 31;
+        }
+    }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && tot) base = atomicAdd(cursor, tot);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const int off = base + incl - n;
+    if (act) t.row[yr] = make_int2(off, n);
+    if (base + tot > CCL2_CAP) return false;
+    if (act && n) {
+        int is = off, ie = off;
+        uint32_t carry = 0, B = win_word<INVERT>(row, 0, ww, wprw);
+        for (int j = 0; j < wprw; j++) {
+            const uint32_t Bn = win_word<INVERT>(row, j + 1, ww, wprw);
+            uint32_t S = B & ~((B << 1) | carry), E = B & ~((B >> 1) | (Bn << 31));
+            carry = B >> 31;
+            while (S) {
+                const int bit = __ffs(S) - 1;
+                S &= S - 1;
+                t.xs[is] = (uint16_t)(32 * j + bit);
+                t.parent[id0 + is] = id0 + is;
+                is++;
+            }
+            while (E) {
+                const int bit = __ffs(E) - 1;
+                E &= E - 1;
+                t.xe[ie++] = (uint16_t)(32 * j + bit);
+            }
+            B = Bn;
+        }
+    }
+    return true;
+}
+
+// unions of the runs of row yr with the runs of row yr - 1 (two sorted lists: one merge walk)
+template <bool CONN8, bool OUTSIDE>
+__device__ __forceinline__ void lane_union(const RunTable &t, int id0, int yr, int y, int w, int h) {
+    const int2 cur = t.row[yr];
+    if (cur.y == 0) return;
+    if (OUTSIDE) {
+        if (y == 0 || y == h - 1) {
+            for (int i = 0; i < cur.y; i++) suf_union(t.parent, id0 + cur.x + i, 0);
+        } else {
+            if (t.xs[cur.x] == 0) suf_union(t.parent, id0 + cur.x, 0);
+            if (t.xe[cur.x + cur.y - 1] == w - 1) suf_union(t.parent, id0 + cur.x + cur.y - 1, 0);
+        }
+    }
+    if (yr == 0) return;
+    const int2 prv = t.row[yr - 1];
+    const int d = CONN8 ? 1 : 0;
+    int i = 0, j = 0;
+    while (i < cur.y && j < prv.y) {
+        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], pxs = t.xs[prv.x + j], pxe = t.xe[prv.x + j];
+        if (pxe < xs - d) j++;
+        else if (pxs > xe + d) i++;
+        else {
+            suf_union(t.parent, id0 + cur.x + i, id0 + prv.x + j);
+            if (pxe < xe) j++; else i++;
+        }
+    }
+}
+
+__device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
+                                                int ylo, int yhi, int jlo, int wprw) {
+    const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrows = yhi - ylo + 1;
+    RunTable bg, fg;
+    bg.row = reinterpret_cast<int2 *>(csm);
+    fg.row = bg.row + a.h;
+    bg.parent = reinterpret_cast<int *>(fg.row + a.h);
+    fg.parent = bg.parent + CCL2_CAP + 2;
+    bg.xs = reinterpret_cast<uint16_t *>(fg.parent + CCL2_CAP + 2);
+    bg.xe = bg.xs + CCL2_CAP;
+    fg.xs = bg.xe + CCL2_CAP;
+    fg.xe = fg.xs + CCL2_CAP;
+    __shared__ int cur_bg, cur_fg, overflow;
+    if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
+    __syncthreads();
+    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
+    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
+
+    // ---- pass 1: background runs (4-connected, linked to the outside) ----
+    for (int r0 = warp * 32; r0 < nrows; r0 += CCL2_THREADS) {
+        const int yr = r0 + lane;
+        const bool act = yr < nrows;
+        if (!lane_extract<true>(dil + (size_t)(ylo + (act ? yr : 0)) * a.wpr, act, yr, 1, bg, &cur_bg, ww, wprw, lane)) overflow = 1;
+    }
+    __syncthreads();
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true>(bg, 1, yr, ylo + yr, ww, a.h);
+    __syncthreads();
+    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
+    for (int r0 = warp * 32; r0 < nrows; r0 += CCL2_THREADS) {
+        const int yr = r0 + lane;
+        const bool act = yr < nrows;
+        uint32_t *frow = fil + (size_t)(ylo + (act ? yr : 0)) * a.wpr;
+        if (act) {
+            const uint32_t *drow = dil + (size_t)(ylo + yr) * a.wpr;
+            for (int j = 0; j < wprw; j++) frow[j] = drow[j];
+            const int2 r = bg.row[yr];
+            for (int i = 0; i < r.y; i++) {
+                if (suf_find(bg.parent, 1 + r.x + i) == 0) continue;       // connected to the outside: not a hole
+                const int xs = bg.xs[r.x + i], xe = bg.xe[r.x + i];
+                for (int j = xs >> 5; j <= (xe >> 5); j++) {
+                    const int lo = max(xs - 32 * j, 0), hi = min(xe - 32 * j, 31);
+                    frow[j] |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                }
+            }
+        }
+        if (!lane_extract<false>(frow, act, yr, 0, fg, &cur_fg, ww, wprw, lane)) overflow = 1;
+    }
+    __syncthreads();
+    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    if (threadIdx.x == 0) heavy[f] = 0;
+    const int total = cur_fg;
+    int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        area2[i] = 0;
+        reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
+    }
+    // ---- pass 2: filled foreground, 8-connected ----
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false>(fg, 0, yr, ylo + yr, ww, a.h);
+    __syncthreads();
+    // ---- per-run bit-quad area and bounding box -> root ----
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) {
+        const int y = ylo + yr;
+        const int2 r = fg.row[yr];
+        const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
+        const uint32_t *lrow = fil + (size_t)y * a.wpr, *urow = lrow - a.wpr;
+        for (int i = 0; i < r.y; i++) {
+            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
+            const int root = suf_find(fg.parent, r.x + i);
+            int q = 0;
+            if (has_up) {
+                const int x0 = max(xs - 1, 0), x1 = xe;         // 2x2 windows owned by this run
+                uint32_t L = win_word<false>(lrow, x0 >> 5, ww, wprw), U = win_word<false>(urow, x0 >> 5, ww, wprw);
+                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
+                    const uint32_t Ln = win_word<false>(lrow, j + 1, ww, wprw), Un = win_word<false>(urow, j + 1, ww, wprw);
+                    const uint32_t l1 = (L >> 1) | (Ln << 31), u1 = (U >> 1) | (Un << 31);
+                    const uint32_t q4 = L & l1 & U & u1, q3 = (L & l1 & (U ^ u1)) | (U & u1 & (L ^ l1));
+                    const int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
+                    const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    q += 2 * __popc(q4 & m) + __popc(q3 & m);
+                    L = Ln; U = Un;
+                }
+            }
+            if (q) atomicAdd(area2 + root, q);
+            int *bb = bbox + (size_t)root * 4;
+            atomicMin(bb + 0, xs);
+            atomicMin(bb + 1, y);
+            atomicMax(bb + 2, xe);
+            atomicMax(bb + 3, y);
+        }
+    }
+    __syncthreads();
+    // ---- roots -> component records ----
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        if (fg.parent[i] != i) continue;
+        const int ar = __ldcg(area2 + i);
+        const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
+        const int slot = atomicAdd(a.ncomp + f, 1);
+        const bool skipped = (2LL * a.max_area < ar) && (ar < 2LL * a.min_area);   // find_motion.py:684
+        if (!skipped) atomicAdd(a.ncounted + f, 1);
+        if (slot < a.maxc) {
+            fm_component c;
+            c.area_x2 = ar; c.x = bb.x + 32 * jlo; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
+            a.comps[(size_t)f * a.maxc + slot] = c;
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
@@ -904,7 +1115,8 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
     }
     const int wprw = jhi - jlo + 1;
-    if (wprw <= 8) ccl_frame_window_g<8>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    if (a.lanes) ccl_frame_lanes(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    else if (wprw <= 8) ccl_frame_window_g<8>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (wprw <= 16) ccl_frame_window_g<16>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (K > 1 && wprw <= 32) ccl_frame_window<1>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (K > 2 && wprw <= 64) ccl_frame_window<2>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
@@ -1026,6 +1238,7 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.plane = plane; a.fill = fill; a.rowrange = rowrange;
         a.raw = raw; a.rawrange = rawrange; a.rangeout = rowrange; a.planeout = const_cast<uint32_t *>(plane);
         a.flatwords = flatwords; a.aligned = (w % 32) == 0;
+        { const char *e = getenv("FM_CCL_LANES"); a.lanes = e ? atoi(e) : 1; }
         a.T = T; a.t0 = t0; a.Th = Th;
         a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
