@@ -43,34 +43,44 @@ __device__ __forceinline__ uint32_t flat_row_word(const uint32_t *flat, int y, i
 // one row of the 5x5 dilation (two iterations of the 3x3 default kernel, out-of-image pixels ignored): lanes hold the
 // words of the row; returns the OR of the lane's words and the lane's first / last non-empty word column
 template <bool ALIGNED>
+__device__ __forceinline__ uint32_t dilate_vor(const uint32_t *__restrict__ flat, int y, int j, int w, int h, int wpr) {
+    // OR of word j over rows y-2 .. y+2 (rows outside the image ignored)
+    uint32_t v = 0;
+    if (j >= wpr) return 0u;
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy++) {
+        const int yy = y + dy;
+        if (ALIGNED) {                  // w % 32 == 0: flat order == row-padded order
+            if ((unsigned)yy < (unsigned)h) v |= __ldcg(flat + (size_t)yy * wpr + j);
+        } else {
+            v |= flat_row_word(flat, yy, j, w, h, wpr);
+        }
+    }
+    return v;
+}
+
+template <bool ALIGNED>
 __device__ __forceinline__ uint32_t dilate_row(const uint32_t *__restrict__ flat, uint32_t *__restrict__ out, int y, int w,
                                                int h, int wpr, int lane, int &jmin, int &jmax) {
-    uint32_t anyw = 0;
-    for (int j = lane; j < wpr; j += 32) {
-        uint32_t vm = 0, vc = 0, vp = 0;    // vertical OR of words j-1, j, j+1
-#pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            int yy = y + dy;
-            if (ALIGNED) {                  // w % 32 == 0: flat order == row-padded order
-                if ((unsigned)yy < (unsigned)h) {
-                    const uint32_t *r = flat + (size_t)yy * wpr;
-                    vc |= __ldcg(r + j);
-                    if (j > 0) vm |= __ldcg(r + j - 1);
-                    if (j + 1 < wpr) vp |= __ldcg(r + j + 1);
-                }
-            } else {
-                vm |= flat_row_word(flat, yy, j - 1, w, h, wpr);
-                vc |= flat_row_word(flat, yy, j, w, h, wpr);
-                vp |= flat_row_word(flat, yy, j + 1, w, h, wpr);
-            }
+    // vertical OR first (5 loads per word), then the horizontal +-2 from the neighbouring lanes' words
+    uint32_t anyw = 0, vprev = 0, vc = dilate_vor<ALIGNED>(flat, y, lane, w, h, wpr);
+    for (int j0 = 0; j0 < wpr; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t vnext = dilate_vor<ALIGNED>(flat, y, j + 32, w, h, wpr);
+        uint32_t vm = __shfl_up_sync(0xffffffffu, vc, 1), vp = __shfl_down_sync(0xffffffffu, vc, 1);
+        const uint32_t pl = __shfl_sync(0xffffffffu, vprev, 31), nf = __shfl_sync(0xffffffffu, vnext, 0);
+        if (lane == 0) vm = pl;
+        if (lane == 31) vp = nf;
+        if (j < wpr) {
+            uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) | (vp << 30);
+            const int rem = w - 32 * j;
+            if (rem < 32) d &= (1u << rem) - 1u;
+            out[j] = d;
+            anyw |= d;
+            if (d) { jmax = j; jmin = min(jmin, j); }
         }
-        uint32_t d = vc | (vc << 1) | (vc << 2) | (vc >> 1) | (vc >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) |
-                     (vp << 30);
-        int rem = w - 32 * j;
-        if (rem < 32) d &= (1u << rem) - 1u;
-        out[j] = d;
-        anyw |= d;
-        if (d) { jmax = j; jmin = min(jmin, j); }
+        vprev = vc;
+        vc = vnext;
     }
     return anyw;
 }
@@ -121,6 +131,7 @@ struct CclArgs {
     uint32_t *planeout;
     int flatwords, aligned;
     int lanes;                 // row-per-lane labelling (ccl_frame_lanes)
+    int stop;                  // DEBUG
     int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
     int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
     int w, h, wpr, cap;
@@ -881,10 +892,13 @@ __device__ __forceinline__ uint32_t win_word(const uint32_t *row, int j, int ww,
     return v;
 }
 
-// runs of the lane's row -> run table (count pass, warp scan for the slots, emit pass); false = table full
+// Runs of rows [r0, r0 + 1024) -> run table, one row per thread: count pass, CTA-wide prefix sum (slots are handed
+// out in ROW ORDER, so run ids grow with the row and a link "run -> run of the row above" always points to a
+// smaller id), emit pass.  Returns false when the table is full.  Called by all threads of the CTA.
 template <bool INVERT>
 __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int yr, int id0, const RunTable &t, int *cursor,
-                                             int ww, int wprw, int lane) {
+                                             int *wsum, int ww, int wprw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n = 0;
     if (act) {
         uint32_t carry = 0;
@@ -900,13 +914,23 @@ __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int 
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane == 31 && tot) base = atomicAdd(cursor, tot);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    const int off = base + incl - n;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    const int wv = wsum[lane];                               // CCL2_WARPS == 32: one total per lane
+    int winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, winc, 31);
+    const int wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+    const int start = *cursor;
+    const int off = start + wbase + incl - n;
+    __syncthreads();                                         // everybody has read wsum and the cursor
+    if (threadIdx.x == 0) *cursor = start + tot;
     if (act) t.row[yr] = make_int2(off, n);
-    if (base + tot > CCL2_CAP) return false;
+    if (start + tot > CCL2_CAP) return false;
     if (act && n) {
         int is = off, ie = off;
         uint32_t carry = 0, B = win_word<INVERT>(row, 0, ww, wprw);
@@ -932,38 +956,58 @@ __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int 
     return true;
 }
 
-// unions of the runs of row yr with the runs of row yr - 1 (two sorted lists: one merge walk)
-template <bool CONN8, bool OUTSIDE>
+// Unions of the runs of row yr with the outside (OUTSIDE: background touching the window / image border, id 0) and
+// with the runs of row yr - 1 (two sorted lists: one merge walk).
+// FIRST pass: every run stores its first partner as its parent -- a plain store, nobody else writes the parent of a
+// run of this row in this pass, and the partner's id is smaller (row order), so no find and no pointer chasing while
+// the 32 x 32 rows of the CTA build their chains concurrently.  REST pass (after the forest has been flattened by
+// pointer jumping): the remaining partners through the lock-free union, whose finds are now one step.
+template <bool CONN8, bool OUTSIDE, bool FIRST>
 __device__ __forceinline__ void lane_union(const RunTable &t, int id0, int yr, int y, int w, int h) {
     const int2 cur = t.row[yr];
     if (cur.y == 0) return;
-    if (OUTSIDE) {
-        if (y == 0 || y == h - 1) {
-            for (int i = 0; i < cur.y; i++) suf_union(t.parent, id0 + cur.x + i, 0);
-        } else {
-            if (t.xs[cur.x] == 0) suf_union(t.parent, id0 + cur.x, 0);
-            if (t.xe[cur.x + cur.y - 1] == w - 1) suf_union(t.parent, id0 + cur.x + cur.y - 1, 0);
+    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
+    const int d = CONN8 ? 1 : 0;
+    int j = 0;
+    for (int i = 0; i < cur.y; i++) {
+        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
+        bool linked = false;
+        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) {
+            if (FIRST) t.parent[id] = 0;
+            linked = true;
+        }
+        while (j < prv.y && (int)t.xe[prv.x + j] < xs - d) j++;
+        for (int q = j; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) {
+            if (!linked) {
+                if (FIRST) t.parent[id] = id0 + prv.x + q;
+                linked = true;
+            } else if (!FIRST) {
+                suf_union(t.parent, id, id0 + prv.x + q);
+            }
         }
     }
-    if (yr == 0) return;
-    const int2 prv = t.row[yr - 1];
-    const int d = CONN8 ? 1 : 0;
-    int i = 0, j = 0;
-    while (i < cur.y && j < prv.y) {
-        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], pxs = t.xs[prv.x + j], pxe = t.xe[prv.x + j];
-        if (pxe < xs - d) j++;
-        else if (pxs > xe + d) i++;
-        else {
-            suf_union(t.parent, id0 + cur.x + i, id0 + prv.x + j);
-            if (pxe < xe) j++; else i++;
+}
+
+// pointer jumping until every run points at its root (called by all threads of the CTA; ids 0 .. n-1)
+__device__ __forceinline__ void flatten_forest(int *parent, int n, int *flag) {
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) *flag = 0;
+        __syncthreads();
+        bool ch = false;
+        for (int i = threadIdx.x; i < n; i += CCL2_THREADS) {
+            const int p = parent[i], gp = parent[p];
+            if (gp != p) { parent[i] = gp; ch = true; }
         }
+        if (ch) *flag = 1;
+        __syncthreads();
+        if (*flag == 0) break;
     }
 }
 
 __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
                                                 int ylo, int yhi, int jlo, int wprw) {
     const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrows = yhi - ylo + 1;
     RunTable bg, fg;
     bg.row = reinterpret_cast<int2 *>(csm);
@@ -974,25 +1018,27 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     bg.xe = bg.xs + CCL2_CAP;
     fg.xs = bg.xe + CCL2_CAP;
     fg.xe = fg.xs + CCL2_CAP;
-    __shared__ int cur_bg, cur_fg, overflow;
+    __shared__ int cur_bg, cur_fg, overflow, flag, wsum[CCL2_WARPS];
     if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
     __syncthreads();
     const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
     uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
 
     // ---- pass 1: background runs (4-connected, linked to the outside) ----
-    for (int r0 = warp * 32; r0 < nrows; r0 += CCL2_THREADS) {
-        const int yr = r0 + lane;
+    for (int r0 = 0; r0 < nrows; r0 += CCL2_THREADS) {
+        const int yr = r0 + threadIdx.x;
         const bool act = yr < nrows;
-        if (!lane_extract<true>(dil + (size_t)(ylo + (act ? yr : 0)) * a.wpr, act, yr, 1, bg, &cur_bg, ww, wprw, lane)) overflow = 1;
+        if (!lane_extract<true>(dil + (size_t)(ylo + (act ? yr : 0)) * a.wpr, act, yr, 1, bg, &cur_bg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true>(bg, 1, yr, ylo + yr, ww, a.h);
-    __syncthreads();
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true, true>(bg, 1, yr, ylo + yr, ww, a.h);
+    flatten_forest(bg.parent, cur_bg + 1, &flag);
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true, false>(bg, 1, yr, ylo + yr, ww, a.h);
+    flatten_forest(bg.parent, cur_bg + 1, &flag);
     // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
-    for (int r0 = warp * 32; r0 < nrows; r0 += CCL2_THREADS) {
-        const int yr = r0 + lane;
+    for (int r0 = 0; r0 < nrows; r0 += CCL2_THREADS) {
+        const int yr = r0 + threadIdx.x;
         const bool act = yr < nrows;
         uint32_t *frow = fil + (size_t)(ylo + (act ? yr : 0)) * a.wpr;
         if (act) {
@@ -1000,7 +1046,7 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
             for (int j = 0; j < wprw; j++) frow[j] = drow[j];
             const int2 r = bg.row[yr];
             for (int i = 0; i < r.y; i++) {
-                if (suf_find(bg.parent, 1 + r.x + i) == 0) continue;       // connected to the outside: not a hole
+                if (bg.parent[1 + r.x + i] == 0) continue;                 // connected to the outside: not a hole
                 const int xs = bg.xs[r.x + i], xe = bg.xe[r.x + i];
                 for (int j = xs >> 5; j <= (xe >> 5); j++) {
                     const int lo = max(xs - 32 * j, 0), hi = min(xe - 32 * j, 31);
@@ -1008,7 +1054,7 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
                 }
             }
         }
-        if (!lane_extract<false>(frow, act, yr, 0, fg, &cur_fg, ww, wprw, lane)) overflow = 1;
+        if (!lane_extract<false>(frow, act, yr, 0, fg, &cur_fg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
@@ -1020,8 +1066,10 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
         reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
     }
     // ---- pass 2: filled foreground, 8-connected ----
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false>(fg, 0, yr, ylo + yr, ww, a.h);
-    __syncthreads();
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false, true>(fg, 0, yr, ylo + yr, ww, a.h);
+    flatten_forest(fg.parent, total, &flag);
+    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false, false>(fg, 0, yr, ylo + yr, ww, a.h);
+    flatten_forest(fg.parent, total, &flag);
     // ---- per-run bit-quad area and bounding box -> root ----
     for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) {
         const int y = ylo + yr;
@@ -1030,7 +1078,7 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
         const uint32_t *lrow = fil + (size_t)y * a.wpr, *urow = lrow - a.wpr;
         for (int i = 0; i < r.y; i++) {
             const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
-            const int root = suf_find(fg.parent, r.x + i);
+            const int root = fg.parent[r.x + i];
             int q = 0;
             if (has_up) {
                 const int x0 = max(xs - 1, 0), x1 = xe;         // 2x2 windows owned by this run
@@ -1115,6 +1163,7 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
     }
     const int wprw = jhi - jlo + 1;
+    if (a.stop == 9) return;
     if (a.lanes) ccl_frame_lanes(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (wprw <= 8) ccl_frame_window_g<8>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
     else if (wprw <= 16) ccl_frame_window_g<16>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
@@ -1239,6 +1288,7 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.raw = raw; a.rawrange = rawrange; a.rangeout = rowrange; a.planeout = const_cast<uint32_t *>(plane);
         a.flatwords = flatwords; a.aligned = (w % 32) == 0;
         { const char *e = getenv("FM_CCL_LANES"); a.lanes = e ? atoi(e) : 1; }
+        { const char *e = getenv("FM_CCL_STOP"); a.stop = e ? atoi(e) : 0; }
         a.T = T; a.t0 = t0; a.Th = Th;
         a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
