@@ -131,6 +131,7 @@ struct CclArgs {
     uint32_t *planeout;
     int flatwords, aligned;
     int lanes;                 // row-per-lane labelling (ccl_frame_lanes)
+    int cache_words;           // shared-memory words available for staging the window rows
     int stop;                  // DEBUG
     int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
     int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
@@ -963,9 +964,10 @@ __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int 
 // the 32 x 32 rows of the CTA build their chains concurrently.  REST pass (after the forest has been flattened by
 // pointer jumping): the remaining partners through the lock-free union, whose finds are now one step.
 template <bool CONN8, bool OUTSIDE, bool FIRST>
-__device__ __forceinline__ void lane_union(const RunTable &t, int id0, int yr, int y, int w, int h) {
+__device__ __forceinline__ bool lane_union(const RunTable &t, int id0, int yr, int y, int w, int h) {
     const int2 cur = t.row[yr];
-    if (cur.y == 0) return;
+    if (cur.y == 0) return false;
+    bool did = false;
     const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
     const int d = CONN8 ? 1 : 0;
     int j = 0;
@@ -983,25 +985,29 @@ __device__ __forceinline__ void lane_union(const RunTable &t, int id0, int yr, i
                 linked = true;
             } else if (!FIRST) {
                 suf_union(t.parent, id, id0 + prv.x + q);
+                did = true;
             }
         }
     }
+    return did;
 }
 
-// pointer jumping until every run points at its root (called by all threads of the CTA; ids 0 .. n-1)
-__device__ __forceinline__ void flatten_forest(int *parent, int n, int *flag) {
+// pointer jumping until every run points at its root (called by all threads of the CTA; ids 0 .. n-1):
+// four hops per round, one barrier-with-vote per round
+__device__ __forceinline__ void flatten_forest(int *parent, int n) {
+    __syncthreads();
     while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) *flag = 0;
-        __syncthreads();
         bool ch = false;
         for (int i = threadIdx.x; i < n; i += CCL2_THREADS) {
-            const int p = parent[i], gp = parent[p];
-            if (gp != p) { parent[i] = gp; ch = true; }
+            const int p = parent[i];
+            int q = parent[p];
+            if (q != p) {
+                q = parent[parent[q]];
+                parent[i] = q;
+                ch = true;
+            }
         }
-        if (ch) *flag = 1;
-        __syncthreads();
-        if (*flag == 0) break;
+        if (!__syncthreads_or(ch)) break;
     }
 }
 
@@ -1018,32 +1024,56 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     bg.xe = bg.xs + CCL2_CAP;
     fg.xs = bg.xe + CCL2_CAP;
     fg.xe = fg.xs + CCL2_CAP;
-    __shared__ int cur_bg, cur_fg, overflow, flag, wsum[CCL2_WARPS];
+    __shared__ int cur_bg, cur_fg, overflow, wsum[CCL2_WARPS];
     if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
     __syncthreads();
-    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
-    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
+    // The window rows are walked seven times by single lanes: when they fit they are staged into shared memory (odd
+    // pitch: lanes of a warp read different rows at the same word index) and the hole filling happens in place;
+    // otherwise the walks go to the planes in global memory (L2).  Generic pointers serve both.
+    uint32_t *cache = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP);
+    const int cpitch = wprw | 1;
+    const bool cached = (size_t)nrows * cpitch <= (size_t)a.cache_words;
+    const uint32_t *dil;
+    uint32_t *fil;
+    size_t pitch;
+    if (cached) {
+        const uint32_t *src = a.plane + ((size_t)f * a.h + ylo) * a.wpr + jlo;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int yr = warp; yr < nrows; yr += CCL2_WARPS)
+            for (int j = lane; j < wprw; j += 32) cache[yr * cpitch + j] = __ldcg(src + (size_t)yr * a.wpr + j);
+        dil = cache; fil = cache; pitch = cpitch;
+        __syncthreads();
+    } else {
+        dil = a.plane + ((size_t)f * a.h + ylo) * a.wpr + jlo;
+        fil = a.fill + ((size_t)f * a.h + ylo) * a.wpr + jlo;
+        pitch = a.wpr;
+    }
 
     // ---- pass 1: background runs (4-connected, linked to the outside) ----
     for (int r0 = 0; r0 < nrows; r0 += CCL2_THREADS) {
         const int yr = r0 + threadIdx.x;
         const bool act = yr < nrows;
-        if (!lane_extract<true>(dil + (size_t)(ylo + (act ? yr : 0)) * a.wpr, act, yr, 1, bg, &cur_bg, wsum, ww, wprw)) overflow = 1;
+        if (!lane_extract<true>(dil + (size_t)(act ? yr : 0) * pitch, act, yr, 1, bg, &cur_bg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
     for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true, true>(bg, 1, yr, ylo + yr, ww, a.h);
-    flatten_forest(bg.parent, cur_bg + 1, &flag);
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true, false>(bg, 1, yr, ylo + yr, ww, a.h);
-    flatten_forest(bg.parent, cur_bg + 1, &flag);
+    flatten_forest(bg.parent, cur_bg + 1);
+    {
+        bool did = false;
+        for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) did |= lane_union<false, true, false>(bg, 1, yr, ylo + yr, ww, a.h);
+        if (__syncthreads_or(did)) flatten_forest(bg.parent, cur_bg + 1);
+    }
     // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
     for (int r0 = 0; r0 < nrows; r0 += CCL2_THREADS) {
         const int yr = r0 + threadIdx.x;
         const bool act = yr < nrows;
-        uint32_t *frow = fil + (size_t)(ylo + (act ? yr : 0)) * a.wpr;
+        uint32_t *frow = fil + (size_t)(act ? yr : 0) * pitch;
         if (act) {
-            const uint32_t *drow = dil + (size_t)(ylo + yr) * a.wpr;
-            for (int j = 0; j < wprw; j++) frow[j] = drow[j];
+            if (!cached) {
+                const uint32_t *drow = dil + (size_t)yr * pitch;
+                for (int j = 0; j < wprw; j++) frow[j] = drow[j];
+            }
             const int2 r = bg.row[yr];
             for (int i = 0; i < r.y; i++) {
                 if (bg.parent[1 + r.x + i] == 0) continue;                 // connected to the outside: not a hole
@@ -1067,15 +1097,18 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     }
     // ---- pass 2: filled foreground, 8-connected ----
     for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false, true>(fg, 0, yr, ylo + yr, ww, a.h);
-    flatten_forest(fg.parent, total, &flag);
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false, false>(fg, 0, yr, ylo + yr, ww, a.h);
-    flatten_forest(fg.parent, total, &flag);
+    flatten_forest(fg.parent, total);
+    {
+        bool did = false;
+        for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) did |= lane_union<true, false, false>(fg, 0, yr, ylo + yr, ww, a.h);
+        if (__syncthreads_or(did)) flatten_forest(fg.parent, total);
+    }
     // ---- per-run bit-quad area and bounding box -> root ----
     for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) {
         const int y = ylo + yr;
         const int2 r = fg.row[yr];
         const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
-        const uint32_t *lrow = fil + (size_t)y * a.wpr, *urow = lrow - a.wpr;
+        const uint32_t *lrow = fil + (size_t)yr * pitch, *urow = lrow - pitch;
         for (int i = 0; i < r.y; i++) {
             const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
             const int root = fg.parent[r.x + i];
@@ -1297,8 +1330,13 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.min_area = min_area; a.max_area = max_area;
         if (wpr <= 128 && heavy) {
             const int K = wpr <= 32 ? 1 : (wpr <= 64 ? 2 : 4);
-            size_t smem = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
-                          (size_t)4 * CCL2_CAP * sizeof(uint16_t) + (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
+            const size_t tables = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
+                                  (size_t)4 * CCL2_CAP * sizeof(uint16_t);
+            const size_t scratch = (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
+            const size_t room = tables < 200 * 1024 ? 200 * 1024 - tables : 0;       // row cache of the row-per-lane path
+            const size_t cacheb = room < 128 * 1024 ? room : 128 * 1024;
+            size_t smem = tables + (scratch > cacheb ? scratch : cacheb);
+            a.cache_words = (int)((smem - tables) / 4);
             static size_t configured_dev[FM_MAX_DEVICES][3] = {{0}};
             int dev = 0;
             cudaGetDevice(&dev);
