@@ -407,6 +407,7 @@ struct RunTable {
     int2 *row;        // [rows] (first slot, run count) of each row
     int *parent;      // [CCL2_CAP + 1]; for the background table id 0 = outside
     uint16_t *xs, *xe;
+    uint16_t *rowof;  // [CCL2_CAP] window row of each run
 };
 
 template <int K, bool INVERT>
@@ -943,6 +944,7 @@ __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int 
                 const int bit = __ffs(S) - 1;
                 S &= S - 1;
                 t.xs[is] = (uint16_t)(32 * j + bit);
+                t.rowof[is] = (uint16_t)yr;
                 t.parent[id0 + is] = id0 + is;
                 is++;
             }
@@ -957,36 +959,37 @@ __device__ __forceinline__ bool lane_extract(const uint32_t *row, bool act, int 
     return true;
 }
 
-// Unions of the runs of row yr with the outside (OUTSIDE: background touching the window / image border, id 0) and
-// with the runs of row yr - 1 (two sorted lists: one merge walk).
-// FIRST pass: every run stores its first partner as its parent -- a plain store, nobody else writes the parent of a
-// run of this row in this pass, and the partner's id is smaller (row order), so no find and no pointer chasing while
-// the 32 x 32 rows of the CTA build their chains concurrently.  REST pass (after the forest has been flattened by
-// pointer jumping): the remaining partners through the lock-free union, whose finds are now one step.
+// Unions of run i (one thread per run: rows with hundreds of runs -- noise at a fading edge -- must not serialise on
+// one lane) with the outside (OUTSIDE: background touching the window / image border, id 0) and with the runs of the
+// row above that it touches (binary search for the first one).
+// FIRST pass: the run stores its first partner as its parent -- a plain store, nobody else writes the parent of
+// this run in this pass, and the partner's id is smaller (row order), so no find and no pointer chasing while the
+// chains are being built concurrently.  REST pass (after the forest has been flattened by pointer jumping): the
+// remaining partners through the lock-free union, whose finds are now one step.  Returns true if it did a union.
 template <bool CONN8, bool OUTSIDE, bool FIRST>
-__device__ __forceinline__ bool lane_union(const RunTable &t, int id0, int yr, int y, int w, int h) {
-    const int2 cur = t.row[yr];
-    if (cur.y == 0) return false;
-    bool did = false;
-    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
+__device__ __forceinline__ bool run_union(const RunTable &t, int id0, int i, int ylo, int w, int h) {
+    const int yr = t.rowof[i], y = ylo + yr;
+    const int xs = t.xs[i], xe = t.xe[i], id = id0 + i;
+    bool linked = false, did = false;
+    if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) {
+        if (FIRST) t.parent[id] = 0;
+        linked = true;
+    }
+    if (yr == 0) return false;
+    const int2 prv = t.row[yr - 1];
     const int d = CONN8 ? 1 : 0;
-    int j = 0;
-    for (int i = 0; i < cur.y; i++) {
-        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
-        bool linked = false;
-        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) {
-            if (FIRST) t.parent[id] = 0;
+    int lo = 0, hi = prv.y;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)t.xe[prv.x + mid] < xs - d) lo = mid + 1; else hi = mid;
+    }
+    for (int q = lo; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) {
+        if (!linked) {
+            if (FIRST) t.parent[id] = id0 + prv.x + q;
             linked = true;
-        }
-        while (j < prv.y && (int)t.xe[prv.x + j] < xs - d) j++;
-        for (int q = j; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) {
-            if (!linked) {
-                if (FIRST) t.parent[id] = id0 + prv.x + q;
-                linked = true;
-            } else if (!FIRST) {
-                suf_union(t.parent, id, id0 + prv.x + q);
-                did = true;
-            }
+        } else if (!FIRST) {
+            suf_union(t.parent, id, id0 + prv.x + q);
+            did = true;
         }
     }
     return did;
@@ -1024,13 +1027,15 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     bg.xe = bg.xs + CCL2_CAP;
     fg.xs = bg.xe + CCL2_CAP;
     fg.xe = fg.xs + CCL2_CAP;
+    bg.rowof = fg.xe + CCL2_CAP;
+    fg.rowof = bg.rowof + CCL2_CAP;
     __shared__ int cur_bg, cur_fg, overflow, wsum[CCL2_WARPS];
     if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
     __syncthreads();
     // The window rows are walked seven times by single lanes: when they fit they are staged into shared memory (odd
     // pitch: lanes of a warp read different rows at the same word index) and the hole filling happens in place;
     // otherwise the walks go to the planes in global memory (L2).  Generic pointers serve both.
-    uint32_t *cache = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP);
+    uint32_t *cache = reinterpret_cast<uint32_t *>(fg.rowof + CCL2_CAP);
     const int cpitch = wprw | 1;
     const bool cached = (size_t)nrows * cpitch <= (size_t)a.cache_words;
     const uint32_t *dil;
@@ -1057,34 +1062,34 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<false, true, true>(bg, 1, yr, ylo + yr, ww, a.h);
-    flatten_forest(bg.parent, cur_bg + 1);
+    const int nbg = cur_bg;
+    for (int i = threadIdx.x; i < nbg; i += CCL2_THREADS) run_union<false, true, true>(bg, 1, i, ylo, ww, a.h);
+    flatten_forest(bg.parent, nbg + 1);
     {
         bool did = false;
-        for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) did |= lane_union<false, true, false>(bg, 1, yr, ylo + yr, ww, a.h);
-        if (__syncthreads_or(did)) flatten_forest(bg.parent, cur_bg + 1);
+        for (int i = threadIdx.x; i < nbg; i += CCL2_THREADS) did |= run_union<false, true, false>(bg, 1, i, ylo, ww, a.h);
+        if (__syncthreads_or(did)) flatten_forest(bg.parent, nbg + 1);
     }
-    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
+    // ---- holes (background runs whose root is not the outside) -> filled plane; then its foreground runs ----
+    if (!cached) {
+        for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS)
+            for (int j = 0; j < wprw; j++) fil[(size_t)yr * pitch + j] = dil[(size_t)yr * pitch + j];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < nbg; i += CCL2_THREADS) {
+        if (bg.parent[1 + i] == 0) continue;                               // connected to the outside: not a hole
+        const int xs = bg.xs[i], xe = bg.xe[i];
+        uint32_t *frow = fil + (size_t)bg.rowof[i] * pitch;
+        for (int j = xs >> 5; j <= (xe >> 5); j++) {
+            const int lo = max(xs - 32 * j, 0), hi = min(xe - 32 * j, 31);
+            atomicOr(frow + j, (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u));
+        }
+    }
+    __syncthreads();
     for (int r0 = 0; r0 < nrows; r0 += CCL2_THREADS) {
         const int yr = r0 + threadIdx.x;
         const bool act = yr < nrows;
-        uint32_t *frow = fil + (size_t)(act ? yr : 0) * pitch;
-        if (act) {
-            if (!cached) {
-                const uint32_t *drow = dil + (size_t)yr * pitch;
-                for (int j = 0; j < wprw; j++) frow[j] = drow[j];
-            }
-            const int2 r = bg.row[yr];
-            for (int i = 0; i < r.y; i++) {
-                if (bg.parent[1 + r.x + i] == 0) continue;                 // connected to the outside: not a hole
-                const int xs = bg.xs[r.x + i], xe = bg.xe[r.x + i];
-                for (int j = xs >> 5; j <= (xe >> 5); j++) {
-                    const int lo = max(xs - 32 * j, 0), hi = min(xe - 32 * j, 31);
-                    frow[j] |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                }
-            }
-        }
-        if (!lane_extract<false>(frow, act, yr, 0, fg, &cur_fg, wsum, ww, wprw)) overflow = 1;
+        if (!lane_extract<false>(fil + (size_t)(act ? yr : 0) * pitch, act, yr, 0, fg, &cur_fg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
     if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
@@ -1096,43 +1101,40 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
         reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
     }
     // ---- pass 2: filled foreground, 8-connected ----
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) lane_union<true, false, true>(fg, 0, yr, ylo + yr, ww, a.h);
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) run_union<true, false, true>(fg, 0, i, ylo, ww, a.h);
     flatten_forest(fg.parent, total);
     {
         bool did = false;
-        for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) did |= lane_union<true, false, false>(fg, 0, yr, ylo + yr, ww, a.h);
+        for (int i = threadIdx.x; i < total; i += CCL2_THREADS) did |= run_union<true, false, false>(fg, 0, i, ylo, ww, a.h);
         if (__syncthreads_or(did)) flatten_forest(fg.parent, total);
     }
-    // ---- per-run bit-quad area and bounding box -> root ----
-    for (int yr = threadIdx.x; yr < nrows; yr += CCL2_THREADS) {
-        const int y = ylo + yr;
-        const int2 r = fg.row[yr];
+    // ---- per-run bit-quad area and bounding box -> root (one thread per run) ----
+    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
+        const int yr = fg.rowof[i], y = ylo + yr;
         const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
         const uint32_t *lrow = fil + (size_t)yr * pitch, *urow = lrow - pitch;
-        for (int i = 0; i < r.y; i++) {
-            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
-            const int root = fg.parent[r.x + i];
-            int q = 0;
-            if (has_up) {
-                const int x0 = max(xs - 1, 0), x1 = xe;         // 2x2 windows owned by this run
-                uint32_t L = win_word<false>(lrow, x0 >> 5, ww, wprw), U = win_word<false>(urow, x0 >> 5, ww, wprw);
-                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
-                    const uint32_t Ln = win_word<false>(lrow, j + 1, ww, wprw), Un = win_word<false>(urow, j + 1, ww, wprw);
-                    const uint32_t l1 = (L >> 1) | (Ln << 31), u1 = (U >> 1) | (Un << 31);
-                    const uint32_t q4 = L & l1 & U & u1, q3 = (L & l1 & (U ^ u1)) | (U & u1 & (L ^ l1));
-                    const int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
-                    const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                    q += 2 * __popc(q4 & m) + __popc(q3 & m);
-                    L = Ln; U = Un;
-                }
+        const int xs = fg.xs[i], xe = fg.xe[i];
+        const int root = fg.parent[i];
+        int q = 0;
+        if (has_up) {
+            const int x0 = max(xs - 1, 0), x1 = xe;         // 2x2 windows owned by this run
+            uint32_t L = win_word<false>(lrow, x0 >> 5, ww, wprw), U = win_word<false>(urow, x0 >> 5, ww, wprw);
+            for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
+                const uint32_t Ln = win_word<false>(lrow, j + 1, ww, wprw), Un = win_word<false>(urow, j + 1, ww, wprw);
+                const uint32_t l1 = (L >> 1) | (Ln << 31), u1 = (U >> 1) | (Un << 31);
+                const uint32_t q4 = L & l1 & U & u1, q3 = (L & l1 & (U ^ u1)) | (U & u1 & (L ^ l1));
+                const int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
+                const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                q += 2 * __popc(q4 & m) + __popc(q3 & m);
+                L = Ln; U = Un;
             }
-            if (q) atomicAdd(area2 + root, q);
-            int *bb = bbox + (size_t)root * 4;
-            atomicMin(bb + 0, xs);
-            atomicMin(bb + 1, y);
-            atomicMax(bb + 2, xe);
-            atomicMax(bb + 3, y);
         }
+        if (q) atomicAdd(area2 + root, q);
+        int *bb = bbox + (size_t)root * 4;
+        atomicMin(bb + 0, xs);
+        atomicMin(bb + 1, y);
+        atomicMax(bb + 2, xe);
+        atomicMax(bb + 3, y);
     }
     __syncthreads();
     // ---- roots -> component records ----
@@ -1331,7 +1333,7 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         if (wpr <= 128 && heavy) {
             const int K = wpr <= 32 ? 1 : (wpr <= 64 ? 2 : 4);
             const size_t tables = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
-                                  (size_t)4 * CCL2_CAP * sizeof(uint16_t);
+                                  (size_t)6 * CCL2_CAP * sizeof(uint16_t);
             const size_t scratch = (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
             const size_t room = tables < 200 * 1024 ? 200 * 1024 - tables : 0;       // row cache of the row-per-lane path
             const size_t cacheb = room < 128 * 1024 ? room : 128 * 1024;
