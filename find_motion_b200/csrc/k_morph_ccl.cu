@@ -11,8 +11,6 @@
 // Both labellings are run-based union-find with one warp per row: lanes hold the 32-bit words
 // of the row, run starts/ends come from shifted-word logic and are enumerated with warp prefix
 // sums, unions are lock-free atomicMin links between runs of adjacent rows.
-#include <cstdlib>
-
 #include "fm_common.cuh"
 
 #define WARPS_PER_BLOCK 8
@@ -130,9 +128,7 @@ struct CclArgs {
     int *rangeout;             //   NULL: `plane` is already dilated
     uint32_t *planeout;
     int flatwords, aligned;
-    int lanes;                 // row-per-lane labelling (ccl_frame_lanes)
     int cache_words;           // shared-memory words available for staging the window rows
-    int stop;                  // DEBUG
     int f0, nf;                // local frames [f0, f0+nf) of the range are in this sub-batch
     int T, t0, Th;             // local frame l -> stream l / Th, frame t0 + l % Th, stored at s*T + t
     int w, h, wpr, cap;
@@ -391,13 +387,18 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const i
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: the same labelling with the run tables and the union-find forests in SHARED memory.
-// Frames whose active rows hold more than CCL2_CAP runs (or planes wider than 4096 px) are flagged
-// "heavy" and left to k_ccl_frame.  All dependent accesses (binary searches over the previous row's
-// runs, find / union pointer chasing) stay on chip; global memory is touched only to stream the bit
-// planes and for the per-root reductions.  Rows get their slots in the run tables from a shared
-// cursor (atomicAdd per row), so there is no counting pass and no prefix scan; the filled plane and
-// the foreground runs are produced in the same sweep that detects the holes.
+// K2: the same labelling with the run tables and the union-find forests in SHARED memory, one CTA per frame.
+// Frames whose active rows hold more than CCL2_CAP runs (or planes wider than 4096 px) are flagged "heavy" and
+// left to k_ccl_frame.  The kernel works on the window of rows and word columns that holds the motion (background
+// touching a window edge is connected to the outside exactly as background touching the image border is: there is
+// no foreground beyond the window to enclose it), staged into shared memory when it fits:
+//   row extraction     one row per lane (a lane walks the words of its row; rows hold a handful of runs, so
+//                      spreading one row over a warp would idle most lanes); slots in row order by a CTA-wide scan
+//   unions             one thread per run: first partner by plain store (ids grow with the row, so the link points
+//                      to a smaller id and nobody chases pointers while 1000 rows build their chains concurrently),
+//                      pointer-jumping flatten, remaining partners by lock-free union, flatten
+//   holes              background runs whose root is not the outside are OR-ed into the plane (in place)
+//   statistics         one thread per run: bit-quad area over the run's 2x2 windows, bounding box -> root
 // ---------------------------------------------------------------------------------------------
 #define CCL2_THREADS 1024
 #define CCL2_WARPS (CCL2_THREADS / 32)
@@ -409,73 +410,6 @@ struct RunTable {
     uint16_t *xs, *xe;
     uint16_t *rowof;  // [CCL2_CAP] window row of each run
 };
-
-template <int K, bool INVERT>
-__device__ __forceinline__ void row_words(const uint32_t *row, int w, int wpr, int lane, uint32_t (&B)[K]) {
-#pragma unroll
-    for (int k = 0; k < K; k++) B[k] = plane_word<INVERT>(row, lane + 32 * k, w, wpr);
-}
-
-template <int K>
-__device__ __forceinline__ void row_starts_ends(const uint32_t (&B)[K], int lane, uint32_t (&S)[K], uint32_t (&E)[K]) {
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        uint32_t up = __shfl_up_sync(0xffffffffu, B[k], 1), dn = __shfl_down_sync(0xffffffffu, B[k], 1);
-        uint32_t cp = k > 0 ? __shfl_sync(0xffffffffu, B[k > 0 ? k - 1 : 0], 31) : 0u;
-        uint32_t cn = k < K - 1 ? __shfl_sync(0xffffffffu, B[k < K - 1 ? k + 1 : k], 0) : 0u;
-        uint32_t Bp = lane ? up : cp, Bn = lane < 31 ? dn : cn;
-        S[k] = B[k] & ~((B[k] << 1) | (Bp >> 31));
-        E[k] = B[k] & ~((B[k] >> 1) | (Bn << 31));
-    }
-}
-
-// append the runs of one row to a run table; returns false if the table is full
-template <int K>
-__device__ __forceinline__ bool row_append(const uint32_t (&S)[K], const uint32_t (&E)[K], int lane, int yr, int id0,
-                                           const RunTable &t, int *cursor) {
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) c += __popc(S[k]);
-    const int n = __reduce_add_sync(0xffffffffu, c);
-    int off = 0;
-    if (lane == 0) {
-        off = n ? atomicAdd(cursor, n) : 0;
-        t.row[yr] = make_int2(off, n);
-    }
-    off = __shfl_sync(0xffffffffu, off, 0);
-    if (n == 0) return true;
-    if (off + n > CCL2_CAP) return false;
-    int base = off, ebase = off;       // a run may start in one 1024-px group and end in the next
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        uint32_t s = S[k], e = E[k];
-        if (!__any_sync(0xffffffffu, (s | e) != 0)) continue;
-        int cs = __popc(s), ce = __popc(e), ps = cs, pe = ce;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int vs = __shfl_up_sync(0xffffffffu, ps, o), ve = __shfl_up_sync(0xffffffffu, pe, o);
-            if (lane >= o) { ps += vs; pe += ve; }
-        }
-        int is = base + ps - cs, ie = ebase + pe - ce;
-        const int x0 = 32 * (lane + 32 * k);
-        while (s) {
-            int bit = __ffs(s) - 1;
-            s &= s - 1;
-            t.xs[is] = (uint16_t)(x0 + bit);
-            t.parent[id0 + is] = id0 + is;
-            is++;
-        }
-        while (e) {
-            int bit = __ffs(e) - 1;
-            e &= e - 1;
-            t.xe[ie] = (uint16_t)(x0 + bit);
-            ie++;
-        }
-        base += __shfl_sync(0xffffffffu, ps, 31);
-        ebase += __shfl_sync(0xffffffffu, pe, 31);
-    }
-    return true;
-}
 
 __device__ __forceinline__ int suf_find(int *parent, int x) {
     int p = parent[x];
@@ -500,388 +434,6 @@ __device__ __forceinline__ void suf_union(int *parent, int a, int b) {
     }
 }
 
-// id0: id of slot 0 (1 for the background table whose id 0 is the outside, 0 for the foreground table)
-template <bool CONN8, bool OUTSIDE>
-__device__ __forceinline__ void srow_union(const RunTable &t, int id0, int yr, int y, int w, int h, int lane) {
-    const int2 cur = t.row[yr];
-    if (cur.y == 0) return;
-    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
-    const int d = CONN8 ? 1 : 0;
-    for (int i = lane; i < cur.y; i += 32) {
-        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
-        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(t.parent, id, 0);
-        if (prv.y) {
-            int lo = 0, hi = prv.y;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if ((int)t.xe[prv.x + mid] < xs - d) lo = mid + 1; else hi = mid;
-            }
-            for (int q = lo; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) suf_union(t.parent, id, id0 + prv.x + q);
-        }
-    }
-}
-
-// One frame.  The labelling runs on the window of word columns [jlo, jlo + wprw) that holds every set pixel (from
-// k_dilate): background that touches a window edge is connected to the outside of the image exactly as background
-// that touches the image border is (there is no foreground beyond the window to enclose it), so the result is
-// identical, and a 1080p / 4K frame whose motion spans <= 1024 columns runs with one word per lane (KW = 1).
-template <int KW>
-__device__ __forceinline__ void ccl_frame_window(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
-                                                 int ylo, int yhi, int jlo, int wprw) {
-    constexpr int K = KW;
-    const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows = yhi - ylo + 1;
-    RunTable bg, fg;
-    bg.row = reinterpret_cast<int2 *>(csm);
-    fg.row = bg.row + a.h;
-    bg.parent = reinterpret_cast<int *>(fg.row + a.h);
-    fg.parent = bg.parent + CCL2_CAP + 2;
-    bg.xs = reinterpret_cast<uint16_t *>(fg.parent + CCL2_CAP + 2);
-    bg.xe = bg.xs + CCL2_CAP;
-    fg.xs = bg.xe + CCL2_CAP;
-    fg.xe = fg.xs + CCL2_CAP;
-    uint32_t *q4s = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP) + warp * (2 * 32 * K);
-    uint32_t *q3s = q4s + 32 * K;
-    __shared__ int cur_bg, cur_fg, overflow;
-    if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
-    __syncthreads();
-    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
-    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
-
-    // ---- pass 1: background runs (4-connected, linked to the outside) ----
-    for (int yr = warp; yr < nrows; yr += 2 * CCL2_WARPS) {          // two rows in flight per warp
-        uint32_t B0[K], B1[K], S[K], E[K];
-        const int yr1 = yr + CCL2_WARPS;
-        row_words<K, true>(dil + (size_t)(ylo + yr) * a.wpr, ww, wprw, lane, B0);
-        if (yr1 < nrows) row_words<K, true>(dil + (size_t)(ylo + yr1) * a.wpr, ww, wprw, lane, B1);
-        row_starts_ends<K>(B0, lane, S, E);
-        if (!row_append<K>(S, E, lane, yr, 1, bg, &cur_bg)) overflow = 1;
-        if (yr1 < nrows) {
-            row_starts_ends<K>(B1, lane, S, E);
-            if (!row_append<K>(S, E, lane, yr1, 1, bg, &cur_bg)) overflow = 1;
-        }
-    }
-    __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<false, true>(bg, 1, yr, ylo + yr, ww, a.h, lane);
-    __syncthreads();
-    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
-        uint32_t F[K], S[K], E[K];
-        row_words<K, false>(dil + (size_t)(ylo + yr) * a.wpr, ww, wprw, lane, F);
-        const int2 r = bg.row[yr];
-        for (int b = 0; b < r.y; b += 32) {
-            const int i = b + lane;
-            bool hole = false;
-            int xs = 0, xe = 0;
-            if (i < r.y) { hole = suf_find(bg.parent, 1 + r.x + i) != 0; xs = bg.xs[r.x + i]; xe = bg.xe[r.x + i]; }
-            uint32_t hm = __ballot_sync(0xffffffffu, hole);
-            while (hm) {
-                const int src = __ffs(hm) - 1;
-                hm &= hm - 1;
-                const int hxs = __shfl_sync(0xffffffffu, xs, src), hxe = __shfl_sync(0xffffffffu, xe, src);
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const int x0 = 32 * (lane + 32 * k);
-                    int lo = max(hxs - x0, 0), hi = min(hxe - x0, 31);
-                    if (lo <= hi) F[k] |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            if (lane + 32 * k < wprw) fil[(size_t)(ylo + yr) * a.wpr + lane + 32 * k] = F[k];
-        row_starts_ends<K>(F, lane, S, E);
-        if (!row_append<K>(S, E, lane, yr, 0, fg, &cur_fg)) overflow = 1;
-    }
-    __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    if (threadIdx.x == 0) heavy[f] = 0;
-    const int total = cur_fg;
-    // per-root accumulators live in the global scratch, indexed by the run slot
-    int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
-    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
-        area2[i] = 0;
-        reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
-    }
-    // ---- pass 2: filled foreground, 8-connected ----
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) srow_union<true, false>(fg, 0, yr, ylo + yr, ww, a.h, lane);
-    __syncthreads();
-    // ---- per-run bit-quad area and bounding box -> root ----
-    // The 2x2-window masks of a row pair are computed word-parallel (lanes hold the words of rows y-1 and y),
-    // parked in the warp's shared scratch, and each run then sums the windows x in [xs-1, xe] it owns.
-    for (int yr = warp; yr < nrows; yr += CCL2_WARPS) {
-        const int y = ylo + yr;
-        const int2 r = fg.row[yr];
-        if (r.y == 0) continue;
-        const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
-        if (has_up) {
-            uint32_t L[K], U[K];
-            row_words<K, false>(fil + (size_t)y * a.wpr, ww, wprw, lane, L);
-            row_words<K, false>(fil + (size_t)(y - 1) * a.wpr, ww, wprw, lane, U);
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                uint32_t ln = __shfl_down_sync(0xffffffffu, L[k], 1), un = __shfl_down_sync(0xffffffffu, U[k], 1);
-                uint32_t lc = k < K - 1 ? __shfl_sync(0xffffffffu, L[k < K - 1 ? k + 1 : k], 0) : 0u;
-                uint32_t uc = k < K - 1 ? __shfl_sync(0xffffffffu, U[k < K - 1 ? k + 1 : k], 0) : 0u;
-                if (lane == 31) { ln = lc; un = uc; }
-                const uint32_t l0 = L[k], l1 = (L[k] >> 1) | (ln << 31), u0 = U[k], u1 = (U[k] >> 1) | (un << 31);
-                q4s[lane + 32 * k] = l0 & l1 & u0 & u1;
-                q3s[lane + 32 * k] = (l0 & l1 & (u0 ^ u1)) | (u0 & u1 & (l0 ^ l1));
-            }
-        }
-        __syncwarp();
-        for (int i = lane; i < r.y; i += 32) {
-            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
-            const int root = suf_find(fg.parent, r.x + i);
-            int q = 0;
-            if (has_up) {
-                const int x0 = max(xs - 1, 0), x1 = xe;         // windows owned by this run
-                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
-                    int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
-                    uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                    q += 2 * __popc(q4s[j] & m) + __popc(q3s[j] & m);
-                }
-            }
-            if (q) atomicAdd(area2 + root, q);
-            int *bb = bbox + (size_t)root * 4;
-            atomicMin(bb + 0, xs);
-            atomicMin(bb + 1, y);
-            atomicMax(bb + 2, xe);
-            atomicMax(bb + 3, y);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    // ---- roots -> component records ----
-    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
-        if (fg.parent[i] != i) continue;
-        const int ar = __ldcg(area2 + i);
-        const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
-        const int slot = atomicAdd(a.ncomp + f, 1);
-        const bool skipped = (2LL * a.max_area < ar) && (ar < 2LL * a.min_area);   // find_motion.py:684
-        if (!skipped) atomicAdd(a.ncounted + f, 1);
-        if (slot < a.maxc) {
-            fm_component c;
-            c.area_x2 = ar; c.x = bb.x + 32 * jlo; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
-            a.comps[(size_t)f * a.maxc + slot] = c;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Narrow windows: G = 8 or 16 lanes per row, 32 / G rows per warp.  The motion of a frame usually spans a few
-// hundred columns, i.e. <= 8 or 16 words; with one row per warp 3/4 or 1/2 of the lanes would idle through every
-// shuffle, scan and table walk.  Same algorithm as ccl_frame_window: lane sl = lane % G holds word sl of the
-// window row of its group; neighbour shuffles stop at the group boundary; scans and broadcasts use the
-// shuffle width G.  Full-mask collectives only (every lane executes every collective; inactive groups carry zeros).
-// ---------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ void g_starts_ends(uint32_t B, int sl, uint32_t &S, uint32_t &E) {
-    const uint32_t up = __shfl_up_sync(0xffffffffu, B, 1), dn = __shfl_down_sync(0xffffffffu, B, 1);
-    const uint32_t Bp = sl ? up : 0u, Bn = sl < G - 1 ? dn : 0u;
-    S = B & ~((B << 1) | (Bp >> 31));
-    E = B & ~((B >> 1) | (Bn << 31));
-}
-
-template <int G>
-__device__ __forceinline__ bool g_append(uint32_t S, uint32_t E, int sl, bool act, int yr, int id0, const RunTable &t,
-                                         int *cursor) {
-    const int cs = __popc(S), ce = __popc(E);
-    int p = cs | (ce << 16);                    // starts and ends scanned together (a row holds < 65536 runs)
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, p, o, G);
-        if (sl >= o) p += v;
-    }
-    const int n = __shfl_sync(0xffffffffu, p, G - 1, G) & 0xffff;      // runs of the row
-    int off = 0;
-    if (sl == 0 && act) {
-        off = n ? atomicAdd(cursor, n) : 0;
-        t.row[yr] = make_int2(off, n);
-    }
-    off = __shfl_sync(0xffffffffu, off, 0, G);
-    if (n == 0) return true;
-    if (off + n > CCL2_CAP) return false;
-    int is = off + (p & 0xffff) - cs, ie = off + (p >> 16) - ce;
-    const int x0 = 32 * sl;
-    while (S) {
-        const int bit = __ffs(S) - 1;
-        S &= S - 1;
-        t.xs[is] = (uint16_t)(x0 + bit);
-        t.parent[id0 + is] = id0 + is;
-        is++;
-    }
-    while (E) {
-        const int bit = __ffs(E) - 1;
-        E &= E - 1;
-        t.xe[ie] = (uint16_t)(x0 + bit);
-        ie++;
-    }
-    return true;
-}
-
-template <bool CONN8, bool OUTSIDE, int G>
-__device__ __forceinline__ void g_union(const RunTable &t, int id0, int yr, int y, int w, int h, int sl) {
-    const int2 cur = t.row[yr];
-    if (cur.y == 0) return;
-    const int2 prv = yr > 0 ? t.row[yr - 1] : make_int2(0, 0);
-    const int d = CONN8 ? 1 : 0;
-    for (int i = sl; i < cur.y; i += G) {
-        const int xs = t.xs[cur.x + i], xe = t.xe[cur.x + i], id = id0 + cur.x + i;
-        if (OUTSIDE && (y == 0 || y == h - 1 || xs == 0 || xe == w - 1)) suf_union(t.parent, id, 0);
-        if (prv.y) {
-            int lo = 0, hi = prv.y;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if ((int)t.xe[prv.x + mid] < xs - d) lo = mid + 1; else hi = mid;
-            }
-            for (int q = lo; q < prv.y && (int)t.xs[prv.x + q] <= xe + d; q++) suf_union(t.parent, id, id0 + prv.x + q);
-        }
-    }
-}
-
-template <int G>
-__device__ __forceinline__ void ccl_frame_window_g(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
-                                                   int ylo, int yhi, int jlo, int wprw) {
-    constexpr int R = 32 / G;                                  // rows per warp
-    const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sl = lane & (G - 1), gi = lane / G;
-    const int nrows = yhi - ylo + 1;
-    RunTable bg, fg;
-    bg.row = reinterpret_cast<int2 *>(csm);
-    fg.row = bg.row + a.h;
-    bg.parent = reinterpret_cast<int *>(fg.row + a.h);
-    fg.parent = bg.parent + CCL2_CAP + 2;
-    bg.xs = reinterpret_cast<uint16_t *>(fg.parent + CCL2_CAP + 2);
-    bg.xe = bg.xs + CCL2_CAP;
-    fg.xs = bg.xe + CCL2_CAP;
-    fg.xe = fg.xs + CCL2_CAP;
-    uint32_t *q4s = reinterpret_cast<uint32_t *>(fg.xe + CCL2_CAP) + warp * 64;
-    uint32_t *q3s = q4s + 32;
-    __shared__ int cur_bg, cur_fg, overflow;
-    if (threadIdx.x == 0) { cur_bg = 0; cur_fg = 0; overflow = 0; bg.parent[0] = 0; }
-    __syncthreads();
-    const uint32_t *dil = a.plane + (size_t)f * a.h * a.wpr + jlo;
-    uint32_t *fil = a.fill + (size_t)f * a.h * a.wpr + jlo;
-
-    // ---- pass 1: background runs (4-connected, linked to the outside) ----
-    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
-        const int yr = base + gi;
-        const bool act = yr < nrows;
-        const uint32_t B = act ? plane_word<true>(dil + (size_t)(ylo + yr) * a.wpr, sl, ww, wprw) : 0u;
-        uint32_t S, E;
-        g_starts_ends<G>(B, sl, S, E);
-        if (!g_append<G>(S, E, sl, act, yr, 1, bg, &cur_bg)) overflow = 1;
-    }
-    __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R)
-        if (base + gi < nrows) g_union<false, true, G>(bg, 1, base + gi, ylo + base + gi, ww, a.h, sl);
-    __syncthreads();
-    // ---- holes -> filled plane, and the foreground runs of the filled rows in the same sweep ----
-    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
-        const int yr = base + gi;
-        const bool act = yr < nrows;
-        uint32_t F = act ? plane_word<false>(dil + (size_t)(ylo + yr) * a.wpr, sl, ww, wprw) : 0u;
-        const int2 r = act ? bg.row[yr] : make_int2(0, 0);
-        const int rmax = __reduce_max_sync(0xffffffffu, r.y);
-        for (int b = 0; b < rmax; b += G) {
-            const int i = b + sl;
-            bool hole = false;
-            int xs = 0, xe = 0;
-            if (i < r.y) { hole = suf_find(bg.parent, 1 + r.x + i) != 0; xs = bg.xs[r.x + i]; xe = bg.xe[r.x + i]; }
-            uint32_t hm = (__ballot_sync(0xffffffffu, hole) >> (gi * G)) & ((1u << G) - 1u);    // holes of this group
-            const int cmax = __reduce_max_sync(0xffffffffu, __popc(hm));
-            for (int q = 0; q < cmax; q++) {
-                const bool has = hm != 0;
-                const int src = has ? __ffs(hm) - 1 : 0;
-                hm &= hm - 1;
-                const int hxs = __shfl_sync(0xffffffffu, xs, src, G), hxe = __shfl_sync(0xffffffffu, xe, src, G);
-                const int lo = max(hxs - 32 * sl, 0), hi = min(hxe - 32 * sl, 31);
-                if (has && lo <= hi) F |= (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            }
-        }
-        if (act && sl < wprw) fil[(size_t)(ylo + yr) * a.wpr + sl] = F;
-        uint32_t S, E;
-        g_starts_ends<G>(F, sl, S, E);
-        if (!g_append<G>(S, E, sl, act, yr, 0, fg, &cur_fg)) overflow = 1;
-    }
-    __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    if (threadIdx.x == 0) heavy[f] = 0;
-    const int total = cur_fg;
-    int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
-    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
-        area2[i] = 0;
-        reinterpret_cast<int4 *>(bbox)[i] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
-    }
-    // ---- pass 2: filled foreground, 8-connected ----
-    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R)
-        if (base + gi < nrows) g_union<true, false, G>(fg, 0, base + gi, ylo + base + gi, ww, a.h, sl);
-    __syncthreads();
-    // ---- per-run bit-quad area and bounding box -> root ----
-    for (int base = warp * R; base < nrows; base += CCL2_WARPS * R) {
-        const int yr = base + gi, y = ylo + yr;
-        const bool act = yr < nrows;
-        const int2 r = act ? fg.row[yr] : make_int2(0, 0);
-        const bool has_up = yr > 0;      // row ylo is empty unless ylo == 0, where there is no row above
-        const bool ld = act && r.y && has_up;
-        const uint32_t L = ld ? plane_word<false>(fil + (size_t)y * a.wpr, sl, ww, wprw) : 0u;
-        const uint32_t U = ld ? plane_word<false>(fil + (size_t)(y - 1) * a.wpr, sl, ww, wprw) : 0u;
-        uint32_t ln = __shfl_down_sync(0xffffffffu, L, 1), un = __shfl_down_sync(0xffffffffu, U, 1);
-        if (sl == G - 1) { ln = 0; un = 0; }
-        const uint32_t l1 = (L >> 1) | (ln << 31), u1 = (U >> 1) | (un << 31);
-        q4s[lane] = L & l1 & U & u1;
-        q3s[lane] = (L & l1 & (U ^ u1)) | (U & u1 & (L ^ l1));
-        __syncwarp();
-        for (int i = sl; i < r.y; i += G) {
-            const int xs = fg.xs[r.x + i], xe = fg.xe[r.x + i];
-            const int root = suf_find(fg.parent, r.x + i);
-            int q = 0;
-            if (has_up) {
-                const int x0 = max(xs - 1, 0), x1 = xe;         // windows owned by this run
-                for (int j = x0 >> 5; j <= (x1 >> 5); j++) {
-                    int lo = max(x0 - 32 * j, 0), hi = min(x1 - 32 * j, 31);
-                    uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                    q += 2 * __popc(q4s[gi * G + j] & m) + __popc(q3s[gi * G + j] & m);
-                }
-            }
-            if (q) atomicAdd(area2 + root, q);
-            int *bb = bbox + (size_t)root * 4;
-            atomicMin(bb + 0, xs);
-            atomicMin(bb + 1, y);
-            atomicMax(bb + 2, xe);
-            atomicMax(bb + 3, y);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    // ---- roots -> component records ----
-    for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
-        if (fg.parent[i] != i) continue;
-        const int ar = __ldcg(area2 + i);
-        const int4 bb = __ldcg(reinterpret_cast<const int4 *>(bbox) + i);
-        const int slot = atomicAdd(a.ncomp + f, 1);
-        const bool skipped = (2LL * a.max_area < ar) && (ar < 2LL * a.min_area);   // find_motion.py:684
-        if (!skipped) atomicAdd(a.ncounted + f, 1);
-        if (slot < a.maxc) {
-            fm_component c;
-            c.area_x2 = ar; c.x = bb.x + 32 * jlo; c.y = bb.y; c.w = bb.z - bb.x + 1; c.h = bb.w - bb.y + 1;
-            a.comps[(size_t)f * a.maxc + slot] = c;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One ROW PER LANE.  Rows of a motion mask hold a handful of runs, so a warp that spreads one row over its lanes
-// spends ~800 instructions per row on shuffles, scans and table walks with most lanes idle.  Here every lane walks
-// the words of its own row sequentially (run extraction, two-pointer unions with the row above, hole filling,
-// bit-quad statistics), 32 rows per warp in parallel; the only warp collective left is the prefix sum that hands
-// out run-table slots.  Same tables, same union-find, same results.
-// ---------------------------------------------------------------------------------------------
 template <bool INVERT>
 __device__ __forceinline__ uint32_t win_word(const uint32_t *row, int j, int ww, int wprw) {
     if ((unsigned)j >= (unsigned)wprw) return 0u;
@@ -1153,7 +705,6 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
     }
 }
 
-template <int K>
 __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
     const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
@@ -1197,14 +748,7 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         jhi = a.rowrange[4 * f + 2];
         jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
     }
-    const int wprw = jhi - jlo + 1;
-    if (a.stop == 9) return;
-    if (a.lanes) ccl_frame_lanes(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
-    else if (wprw <= 8) ccl_frame_window_g<8>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
-    else if (wprw <= 16) ccl_frame_window_g<16>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
-    else if (K > 1 && wprw <= 32) ccl_frame_window<1>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
-    else if (K > 2 && wprw <= 64) ccl_frame_window<2>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
-    else ccl_frame_window<K>(a, heavy, csm, f, lf, ylo, yhi, jlo, wprw);
+    ccl_frame_lanes(a, heavy, csm, f, lf, ylo, yhi, jlo, jhi - jlo + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1322,8 +866,6 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.plane = plane; a.fill = fill; a.rowrange = rowrange;
         a.raw = raw; a.rawrange = rawrange; a.rangeout = rowrange; a.planeout = const_cast<uint32_t *>(plane);
         a.flatwords = flatwords; a.aligned = (w % 32) == 0;
-        { const char *e = getenv("FM_CCL_LANES"); a.lanes = e ? atoi(e) : 1; }
-        { const char *e = getenv("FM_CCL_STOP"); a.stop = e ? atoi(e) : 0; }
         a.T = T; a.t0 = t0; a.Th = Th;
         a.f0 = f0; a.nf = nf; a.w = w; a.h = h; a.wpr = wpr; a.cap = sc.cap; a.slots = sc.slots;
         a.xs = sc.xs; a.xe = sc.xe; a.rowcnt = sc.rowcnt; a.parent = sc.parent; a.area2 = sc.area2;
@@ -1331,28 +873,20 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
         a.min_area = min_area; a.max_area = max_area;
         if (wpr <= 128 && heavy) {
-            const int K = wpr <= 32 ? 1 : (wpr <= 64 ? 2 : 4);
             const size_t tables = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
                                   (size_t)6 * CCL2_CAP * sizeof(uint16_t);
-            const size_t scratch = (size_t)CCL2_WARPS * 2 * 32 * K * sizeof(uint32_t);
-            const size_t room = tables < 200 * 1024 ? 200 * 1024 - tables : 0;       // row cache of the row-per-lane path
-            const size_t cacheb = room < 128 * 1024 ? room : 128 * 1024;
-            size_t smem = tables + (scratch > cacheb ? scratch : cacheb);
+            const size_t room = tables < 200 * 1024 ? 200 * 1024 - tables : 0;       // shared-memory row cache
+            const size_t smem = tables + (room < 128 * 1024 ? room : 128 * 1024);
             a.cache_words = (int)((smem - tables) / 4);
-            static size_t configured_dev[FM_MAX_DEVICES][3] = {{0}};
+            static size_t configured_dev[FM_MAX_DEVICES] = {0};
             int dev = 0;
             cudaGetDevice(&dev);
-            size_t *configured = configured_dev[dev % FM_MAX_DEVICES];
-            const int ki = K == 1 ? 0 : (K == 2 ? 1 : 2);
-            if (smem > configured[ki]) {
-                if (K == 1) FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                else if (K == 2) FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                else FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured[ki] = smem;
+            size_t &configured = configured_dev[dev % FM_MAX_DEVICES];
+            if (smem > configured) {
+                FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
             }
-            if (K == 1) k_ccl_frame_smem<1><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
-            else if (K == 2) k_ccl_frame_smem<2><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
-            else k_ccl_frame_smem<4><<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
