@@ -127,7 +127,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
     cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
-    cudaFree(c->any); cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->ncounted); cudaFree(c->comps); cudaFree(c->stats);
+    cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
     cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->stage_dev);
     fm_ccl_free(&c->ccl);
     if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
@@ -269,11 +269,13 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->tflat, (F * flatw + FM_TILE_WORDS) * 4);
     ALLOC(c->dil, F * c->h * c->wpr * 4);
     ALLOC(c->fill, F * c->h * c->wpr * 4);
-    ALLOC(c->any, F * 4 * sizeof(int));      // per frame: row and word-column range of the dilated mask
-    ALLOC(c->ncomp, F * sizeof(int));
+    // ranges of the raw ([F][2]) and of the dilated mask ([F][4]) share one allocation, and so do the two counters:
+    // one memset each per call
+    ALLOC(c->rawrange, F * 6 * sizeof(int));
+    c->any = c->rawrange + 2 * F;
+    ALLOC(c->ncomp, F * 2 * sizeof(int));
+    c->ncounted = c->ncomp + F;
     ALLOC(c->heavy, F * sizeof(int));
-    ALLOC(c->rawrange, F * 2 * sizeof(int));
-    ALLOC(c->ncounted, F * sizeof(int));
     ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
     ALLOC(c->stats, F * sizeof(fm_frame_stats));
     ALLOC(c->state, (size_t)c->S * sizeof(StreamState));
@@ -363,7 +365,11 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
     const bool fused = c->fused;
-    FM_CUDA(cudaMemsetAsync(c->rawrange, 0xFF, (size_t)c->S * n_frames * 2 * sizeof(int), st));
+    {   // per-frame result slots of the call: ranges = -1 (nothing set), counters = 0
+        const size_t Fmax = (size_t)c->S * c->Tmax;
+        FM_CUDA(cudaMemsetAsync(c->rawrange, 0xFF, Fmax * 6 * sizeof(int), st));
+        FM_CUDA(cudaMemsetAsync(c->ncomp, 0, Fmax * 2 * sizeof(int), st));
+    }
     cudaEvent_t *ev = nullptr;
     if (c->timing) {
         if (c->ev_pending == FM_TIMING_RING && (rc = timing_drain(c))) return rc;

@@ -899,21 +899,15 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
     return FM_OK;
 }
 
-// clears the per-frame result slots of a call (row ranges, counts); once per call, before any range
-int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st) {
-    const int F = c->S * T;
-    FM_CUDA(cudaMemsetAsync(c->any, 0xFF, (size_t)F * 4 * sizeof(int), st));     // row / column ranges: -1
-    FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (size_t)F * sizeof(int), st));
-    FM_CUDA(cudaMemsetAsync(c->ncounted, 0, (size_t)F * sizeof(int), st));
-    return FM_OK;
-}
+// the per-frame result slots of a call (ranges, counts) are cleared by fm_process before the front end runs
+int fm_launch_morph_begin(fm_ctx *, int, cudaStream_t) { return FM_OK; }
 
 // dilation + contours of frames [t0, t0+Th) of every stream of a T-frame call
 int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st) {
     const int F = c->S * Th;
     // With enough frames to fill the GPU (one CTA per frame) the shared-memory labelling kernel dilates the raw
     // threshold bits of its frame itself; with few frames the grid-wide k_dilate (one warp per row) is faster.
-    if (c->wpr <= 128 && F >= 64)
+    if (c->wpr <= 128 && F >= 32)
         return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
                        c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st, c->tflat,
                        c->rawrange, c->ntiles * FM_TILE_WORDS);
