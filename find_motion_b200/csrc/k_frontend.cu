@@ -259,9 +259,12 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_warp(K0Params p,
 // Same decomposition for 4-byte aligned rows: every lane walks its taps in groups of 4 source pixels
 // (12 bytes = three aligned 32-bit shared loads), the tap list padded to group boundaries with zero
 // weights (x + 0*y == x exactly, so the strictly ordered float32 chains are unchanged).  Bytes become
-// floats with PRMT into the mantissa of 2^23 and one FADD -- no byte loads, no XU conversions.
-__device__ __forceinline__ float byte_f32(uint32_t w, int i) {
-    return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)i)), -8388608.0f);
+// floats with PRMT into the mantissa of 2^23 -- no byte loads, no XU conversions -- and the bias leaves
+// inside the tap product.
+// rn(byte * a) in one FFMA: (2^23 + byte) * a - 2^23 * a is exactly byte * a before the single rounding (2^23 * a is
+// exact), i.e. the same float32 as the reference's unfused product; na = -(2^23 * a)
+__device__ __forceinline__ float byte_mul(uint32_t w, int i, float a, float na) {
+    return __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)i)), a, na);
 }
 
 struct K0GParams {
@@ -354,18 +357,20 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         for (int g = 0; g < gn; g++) {
             const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
             const float4 a = __ldg(gw + g);
-            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W0, 0), a.x));
-            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W0, 1), a.x));
-            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W0, 2), a.x));
-            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W0, 3), a.y));
-            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W1, 0), a.y));
-            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W1, 1), a.y));
-            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W1, 2), a.z));
-            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W1, 3), a.z));
-            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W2, 0), a.z));
-            b0 = __fadd_rn(b0, __fmul_rn(byte_f32(W2, 1), a.w));
-            b1 = __fadd_rn(b1, __fmul_rn(byte_f32(W2, 2), a.w));
-            b2 = __fadd_rn(b2, __fmul_rn(byte_f32(W2, 3), a.w));
+            const float nx = __fmul_rn(a.x, -8388608.0f), ny = __fmul_rn(a.y, -8388608.0f);
+            const float nz = __fmul_rn(a.z, -8388608.0f), nw = __fmul_rn(a.w, -8388608.0f);
+            b0 = __fadd_rn(b0, byte_mul(W0, 0, a.x, nx));
+            b1 = __fadd_rn(b1, byte_mul(W0, 1, a.x, nx));
+            b2 = __fadd_rn(b2, byte_mul(W0, 2, a.x, nx));
+            b0 = __fadd_rn(b0, byte_mul(W0, 3, a.y, ny));
+            b1 = __fadd_rn(b1, byte_mul(W1, 0, a.y, ny));
+            b2 = __fadd_rn(b2, byte_mul(W1, 1, a.y, ny));
+            b0 = __fadd_rn(b0, byte_mul(W1, 2, a.z, nz));
+            b1 = __fadd_rn(b1, byte_mul(W1, 3, a.z, nz));
+            b2 = __fadd_rn(b2, byte_mul(W2, 0, a.z, nz));
+            b0 = __fadd_rn(b0, byte_mul(W2, 1, a.w, nw));
+            b1 = __fadd_rn(b1, byte_mul(W2, 2, a.w, nw));
+            b2 = __fadd_rn(b2, byte_mul(W2, 3, a.w, nw));
         }
         if (j == 0) {
             s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
