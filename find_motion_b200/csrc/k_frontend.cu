@@ -283,6 +283,7 @@ __device__ __noinline__ void copy_partial_block(unsigned char *d, const uint8_t 
     }
 }
 
+#define K0_RG 7         // tap groups per destination column held in registers
 // PF = 16-byte blocks per lane of one source segment (registers used to prefetch the next row)
 template <int PF>
 __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K0GParams gp, int segpitch, int tasks,
@@ -344,6 +345,18 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         }
         return mis;
     };
+    // columns with at most K0_RG tap groups (1080p -> 100: 6) keep weights and bias terms in registers
+    const bool inreg = __all_sync(0xffffffffu, gn <= K0_RG);
+    float4 wr[K0_RG], wn[K0_RG];
+    if (inreg) {
+#pragma unroll
+        for (int g = 0; g < K0_RG; g++) {
+            const float4 a = g < gn ? __ldg(gw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wr[g] = a;
+            wn[g] = make_float4(__fmul_rn(a.x, -8388608.0f), __fmul_rn(a.y, -8388608.0f), __fmul_rn(a.z, -8388608.0f),
+                                __fmul_rn(a.w, -8388608.0f));
+        }
+    }
     issue(0);
     for (int j = 0; j < ny; j++) {
         const float beta = p.ywt[y0 + j];
@@ -353,25 +366,32 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         if (j + 1 < ny) issue(j + 1);
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(rowbuf + mis - b_lo + 3 * gs);
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#define FM_G4(W0, W1, W2, a, n)                                                                               \
+        b0 = __fadd_rn(b0, byte_mul(W0, 0, a.x, n.x)); b1 = __fadd_rn(b1, byte_mul(W0, 1, a.x, n.x));       \
+        b2 = __fadd_rn(b2, byte_mul(W0, 2, a.x, n.x)); b0 = __fadd_rn(b0, byte_mul(W0, 3, a.y, n.y));       \
+        b1 = __fadd_rn(b1, byte_mul(W1, 0, a.y, n.y)); b2 = __fadd_rn(b2, byte_mul(W1, 1, a.y, n.y));       \
+        b0 = __fadd_rn(b0, byte_mul(W1, 2, a.z, n.z)); b1 = __fadd_rn(b1, byte_mul(W1, 3, a.z, n.z));       \
+        b2 = __fadd_rn(b2, byte_mul(W2, 0, a.z, n.z)); b0 = __fadd_rn(b0, byte_mul(W2, 1, a.w, n.w));       \
+        b1 = __fadd_rn(b1, byte_mul(W2, 2, a.w, n.w)); b2 = __fadd_rn(b2, byte_mul(W2, 3, a.w, n.w));
+        if (inreg) {            // the column's weights live in registers for all source rows
+#pragma unroll
+            for (int g = 0; g < K0_RG; g++) {
+                if (g < gn) {
+                    const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
+                    FM_G4(W0, W1, W2, wr[g], wn[g])
+                }
+            }
+        } else {
 #pragma unroll 2
-        for (int g = 0; g < gn; g++) {
-            const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
-            const float4 a = __ldg(gw + g);
-            const float nx = __fmul_rn(a.x, -8388608.0f), ny = __fmul_rn(a.y, -8388608.0f);
-            const float nz = __fmul_rn(a.z, -8388608.0f), nw = __fmul_rn(a.w, -8388608.0f);
-            b0 = __fadd_rn(b0, byte_mul(W0, 0, a.x, nx));
-            b1 = __fadd_rn(b1, byte_mul(W0, 1, a.x, nx));
-            b2 = __fadd_rn(b2, byte_mul(W0, 2, a.x, nx));
-            b0 = __fadd_rn(b0, byte_mul(W0, 3, a.y, ny));
-            b1 = __fadd_rn(b1, byte_mul(W1, 0, a.y, ny));
-            b2 = __fadd_rn(b2, byte_mul(W1, 1, a.y, ny));
-            b0 = __fadd_rn(b0, byte_mul(W1, 2, a.z, nz));
-            b1 = __fadd_rn(b1, byte_mul(W1, 3, a.z, nz));
-            b2 = __fadd_rn(b2, byte_mul(W2, 0, a.z, nz));
-            b0 = __fadd_rn(b0, byte_mul(W2, 1, a.w, nw));
-            b1 = __fadd_rn(b1, byte_mul(W2, 2, a.w, nw));
-            b2 = __fadd_rn(b2, byte_mul(W2, 3, a.w, nw));
+            for (int g = 0; g < gn; g++) {
+                const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
+                const float4 a = __ldg(gw + g);
+                const float4 n = make_float4(__fmul_rn(a.x, -8388608.0f), __fmul_rn(a.y, -8388608.0f),
+                                             __fmul_rn(a.z, -8388608.0f), __fmul_rn(a.w, -8388608.0f));
+                FM_G4(W0, W1, W2, a, n)
+            }
         }
+#undef FM_G4
         if (j == 0) {
             s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
         } else {
