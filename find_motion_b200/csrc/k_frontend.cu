@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
     const int b_lo = gp.g4start[dxa] * 3;
     const int b_hi = min((gp.g4start[dxb - 1] + 4 * gp.g4n[dxb - 1]) * 3, rowbytes);
     const int nbytes = b_hi - b_lo;
-    int gs = 0, gn = 0;
+    int gs = b_lo / 3, gn = 0;          // idle lanes walk the start of the segment with zero weights
     const float4 *gw = gp.g4w;
     if (live) { gs = gp.g4start[dx]; gn = gp.g4n[dx]; gw += gp.g4off[dx]; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         return mis;
     };
     // columns with at most K0_RG tap groups (1080p -> 100: 6) keep weights and bias terms in registers
-    const bool inreg = __all_sync(0xffffffffu, gn <= K0_RG);
+    const int gmax = __reduce_max_sync(0xffffffffu, gn);
+    const bool inreg = gmax <= K0_RG;
     float4 wr[K0_RG], wn[K0_RG];
     if (inreg) {
 #pragma unroll
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         if (inreg) {            // the column's weights live in registers for all source rows
 #pragma unroll
             for (int g = 0; g < K0_RG; g++) {
-                if (g < gn) {
+                if (g < gmax) {     // warp-uniform: lanes with fewer groups add exact zeros (zero weights, finite bytes)
                     const uint32_t W0 = wp[3 * g], W1 = wp[3 * g + 1], W2 = wp[3 * g + 2];
                     FM_G4(W0, W1, W2, wr[g], wn[g])
                 }
