@@ -305,12 +305,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
             // must start 16 B aligned) and so are the gray rows (36 words): unit u is raw + 4 + 12 u -> sg[u].
             // Lanes read words 3 apart: conflict-free.
             const unsigned char *rs = raw + (t & 1) * RAW_STAGE + 4;
+            // two units (8 pixels, 24 bytes -> 2 gray words) per step: half the address arithmetic and loop control
 #pragma unroll
-            for (int i = 0; i < (FG_ROWS * FG_WORDS + FUSED_THREADS - 1) / FUSED_THREADS; i++) {
+            for (int i = 0; i < (FG_ROWS * FG_WORDS / 2 + FUSED_THREADS - 1) / FUSED_THREADS; i++) {
                 int u = tid + i * FUSED_THREADS;
-                if (u < FG_ROWS * FG_WORDS) {
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + u * 12);
-                    sg[u] = gray4(q[0], q[1], q[2]);
+                if (u < FG_ROWS * FG_WORDS / 2) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + u * 24);
+                    const uint32_t g0 = gray4(q[0], q[1], q[2]), g1 = gray4(q[3], q[4], q[5]);
+                    *reinterpret_cast<uint2 *>(sg + 2 * u) = make_uint2(g0, g1);
                 }
             }
         }
