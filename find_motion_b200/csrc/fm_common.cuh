@@ -56,6 +56,7 @@ struct fm_ctx {
     ResizeTab xtab, ytab;
     int *g4start, *g4n, *g4off;   // x taps regrouped in 4-pixel groups with zero-weight padding (k_resize_gray_g4)
     float4 *g4w;
+    int g4max;                    // most tap groups of any destination column
     // planes
     uint8_t *gray;             // [S][Tmax][h][w]
     uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or the low/high byte planes of k_wide.cu

@@ -229,6 +229,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
                 }
                 if ((rc = upload(&c->g4start, g4s))) return fail(rc);
                 if ((rc = upload(&c->g4n, g4n))) return fail(rc);
+                c->g4max = 0;
+                for (int v : g4n) c->g4max = std::max(c->g4max, v);
                 if ((rc = upload(&c->g4off, g4o))) return fail(rc);
                 if ((rc = upload(&c->g4w, g4w))) return fail(rc);
             }

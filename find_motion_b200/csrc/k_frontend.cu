@@ -285,7 +285,7 @@ __device__ __noinline__ void copy_partial_block(unsigned char *d, const uint8_t 
 
 #define K0_RG 7         // tap groups per destination column held in registers
 // PF = 16-byte blocks per lane of one source segment (registers used to prefetch the next row)
-template <int PF>
+template <int PF, bool INREG>
 __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K0GParams gp, int segpitch, int tasks,
                                                                    int nq, int dxw) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -346,9 +346,10 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
         return mis;
     };
     // columns with at most K0_RG tap groups (1080p -> 100: 6) keep weights and bias terms in registers
+    // (INREG: chosen by the host when every column has at most K0_RG groups)
     const int gmax = __reduce_max_sync(0xffffffffu, gn);
-    const bool inreg = gmax <= K0_RG;
-    float4 wr[K0_RG], wn[K0_RG];
+    constexpr bool inreg = INREG;
+    float4 wr[INREG ? K0_RG : 1], wn[INREG ? K0_RG : 1];
     if (inreg) {
 #pragma unroll
         for (int g = 0; g < K0_RG; g++) {
@@ -500,19 +501,29 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                 static size_t configured_g_dev[FM_MAX_DEVICES] = {0};
                 size_t &configured_g = configured_g_dev[c->cfg.device % FM_MAX_DEVICES];
                 if (smemw > configured_g) {
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
                     configured_g = smemw;
                 }
                 K0GParams gp;
                 gp.g4start = c->g4start; gp.g4n = c->g4n; gp.g4off = c->g4off; gp.g4w = c->g4w;
                 const int blocks16 = segpitch / 16 + 1;         // upper bound of 16-byte blocks per segment
                 const int gridw = (tasks + K0W_WARPS - 1) / K0W_WARPS;
-                if (blocks16 <= 4 * 32) k_resize_gray_g4<4><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
-                else if (blocks16 <= 8 * 32) k_resize_gray_g4<8><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
-                else if (blocks16 <= 16 * 32) k_resize_gray_g4<16><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);
+                const bool inreg = c->g4max <= K0_RG;
+#define FM_K0(PF)                                                                                                   \
+                do {                                                                                                \
+                    if (inreg) k_resize_gray_g4<PF, true><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw); \
+                    else k_resize_gray_g4<PF, false><<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, gp, segpitch, tasks, nq, dxw);     \
+                } while (0)
+                if (blocks16 <= 4 * 32) FM_K0(4);
+                else if (blocks16 <= 8 * 32) FM_K0(8);
+                else if (blocks16 <= 16 * 32) FM_K0(16);
                 else k_resize_gray_warp<<<gridw, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
+#undef FM_K0
             } else {
                 k_resize_gray_warp<<<(tasks + K0W_WARPS - 1) / K0W_WARPS, 32 * K0W_WARPS, smemw, st>>>(p, segpitch, tasks, nq, dxw);
             }
