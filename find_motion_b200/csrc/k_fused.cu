@@ -124,8 +124,7 @@ __device__ __forceinline__ int bg8_magic(double b) {
 // bits = 2 * bits + (d > thr2) in two instructions: d + ~thr2 carries out exactly when d > thr2 (unsigned), and the
 // carry is shifted into the accumulator by an add-with-carry.
 __device__ __forceinline__ void push_gt(uint32_t &bits, uint32_t d, uint32_t nthr2) {
-    uint32_t tmp;
-    asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits), "=r"(tmp) : "r"(d), "r"(nthr2));
+    asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits) : "r"(d), "r"(nthr2));
 }
 
 // 8x8 transpose of 4-bit elements across the 8 lanes of a lane octet: in: lane i holds e[r] (nibble r)
@@ -299,11 +298,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
             tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, p.t0 + t + 1, s);
         }
         mbar_wait(&bars[t & 1], (t >> 1) & 1);
-        // ---- staged BGR -> gray bytes in shared memory (tile + halo), 4 pixels per unit ----
+        // ---- staged BGR -> gray bytes in shared memory (tile + halo) ----
         {
-            // the staged rows are dense (pitch 432 B = 36 units of 12 B, first unit at byte 4 because the TMA box
-            // must start 16 B aligned) and so are the gray rows (36 words): unit u is raw + 4 + 12 u -> sg[u].
-            // Lanes read words 3 apart: conflict-free.
+            // the staged rows are dense (pitch 432 B = 36 groups of 4 pixels = 12 B, the first at byte 4 because the
+            // TMA box must start 16 B aligned) and so are the gray rows (36 words): group u is raw + 4 + 12 u -> sg[u].
             const unsigned char *rs = raw + (t & 1) * RAW_STAGE + 4;
             // two units (8 pixels, 24 bytes -> 2 gray words) per step: half the address arithmetic and loop control
 #pragma unroll
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         else if (M) bits = fused_rows<KEEP, SAFE, false, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
         else if (p.shift == 8) bits = fused_rows<KEEP, SAFE, false, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
         else bits = fused_rows<KEEP, SAFE, false, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        // ---- 8 lanes x 8 rows of nibbles -> one 32-pixel word per lane, coalesced store ----
+        // ---- 8 lanes x FT_RPT rows of nibbles -> one 32-pixel word per lane, coalesced store ----
 #if FT_RPT == 4
         // a thread has 4 rows: two frames share one transpose (rows 0-3 = frame t-1, rows 4-7 = frame t)
         if (!(t & 1) && t + 1 < p.T) {
@@ -395,7 +393,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
             if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
         }
 #endif
-        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 8 rows hold something
+        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's FT_RPT rows hold something
             int *rr = p.rawrange + 2 * ((size_t)s * p.Ttot + p.t0 + t);
             atomicMax(rr, min(py + FT_RPT - 1, h - 1));
             atomicMax(rr + 1, h - 1 - py);

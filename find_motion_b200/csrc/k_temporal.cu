@@ -42,9 +42,8 @@ __device__ __forceinline__ uint32_t fm_temporal16(const uint32_t (&px)[4], doubl
             if (INIT) b[j] = X - 4503599627370496.0;
             const int q = __float_as_int(__fadd_rn(__double2float_rn(b[j]), 12582912.0f));     // 0x4B400000 + bg8
             // bits = 2 * bits + (|bg8 - blur| > threshold): q - qoff - src in [0, 2 thr] unless above the threshold
-            uint32_t tmp;
-            asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}"
-                : "+r"(bits), "=r"(tmp) : "r"((uint32_t)(q - qoff - (int)src)), "r"(nthr2));
+            asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}"
+                : "+r"(bits) : "r"((uint32_t)(q - qoff - (int)src)), "r"(nthr2));
             b[j] = __fma_rn(b[j], beta, __fma_rn(X, alpha, nC));
         } else {
             const double sd = fm_u8_to_f64(src);

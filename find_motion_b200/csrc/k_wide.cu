@@ -423,8 +423,7 @@ __device__ __forceinline__ uint32_t wt_temporal4(const int (&lo)[4], const int (
         const double X = __hiloint2double(0x43300000, (int)sv);                     // 2^52 + blur
         if (INIT) bg[j] = X - 4503599627370496.0;
         const int q = __float_as_int(__fadd_rn(__double2float_rn(bg[j]), 12582912.0f));
-        uint32_t tmp;
-        asm("{\n add.cc.u32 %1, %2, %3;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits), "=r"(tmp) : "r"((uint32_t)(q - qoff - (int)sv)), "r"(nthr2));
+        asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits) : "r"((uint32_t)(q - qoff - (int)sv)), "r"(nthr2));
         bg[j] = __fma_rn(bg[j], beta, __fma_rn(X, alpha, nC));
     }
     return __brev(bits) >> 28;       // bit j = pixel j
