@@ -121,13 +121,13 @@ def hbm_peak():
 
 def ncu_traffic(args, info, dom):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same workload (profiles/r2q_fused_ncu_full.json); null if the
+    `ncu --set full` capture of this same workload (profiles/r1r_fused_ncu_full.json); null if the
     workload differs from the captured one."""
     try:
         if dom != "front_end" or (W, H, args.streams, args.frames, args.mode) != (1920, 1080, 8, 16, "full") or \
                 info["gaussian"] > 5:
             return None
-        with open(os.path.join(ROOT, "profiles", "r2q_fused_ncu_full.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1r_fused_ncu_full.json")) as f:
             return int(json.load(f)["traffic_bytes_per_launch"])
     except Exception:
         return None
