@@ -30,7 +30,7 @@ class fm_info(C.Structure):
         ("proc_width", C.c_int32), ("proc_height", C.c_int32), ("gaussian", C.c_int32),
         ("min_area", C.c_int32), ("max_area", C.c_int32), ("cache_frames", C.c_int32),
         ("min_movement_frames", C.c_int32), ("words_per_row", C.c_int32), ("scale", C.c_double),
-        ("front_end", C.c_int32), ("reserved", C.c_int32),
+        ("front_end", C.c_int32), ("max_components", C.c_int32),
     ]
 
 
@@ -45,7 +45,6 @@ class fm_component(C.Structure):
 
 FLAG_KEEP_PLANES = 1
 FLAG_NO_FUSED = 2
-FLAG_OVERLAP = 4
 
 # every symbol include/fm_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -58,7 +57,14 @@ SYMBOLS = {
     "fm_ctx_set_masks": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fm_ctx_reset": (C.c_int, [_P, C.c_int]),
     "fm_process": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P, _P]),
+    "fm_process_ragged": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P, _P, _P]),
     "fm_process_host": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P]),
+    "fm_submit_host": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_size_t, C.c_int, _P]),
+    "fm_wait": (C.c_int, [_P, C.c_int, _P]),
+    "fm_submit_reset": (C.c_int, [_P, C.c_int]),
+    "fm_host_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_int)]),
+    "fm_host_free": (C.c_int, [_P]),
+    "fm_ctx_check": (C.c_int, [_P]),
     "fm_get_components": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(fm_component), C.POINTER(C.c_int)]),
     "fm_debug_planes": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fm_debug_mask": (C.c_int, [_P, C.c_int, _P]),

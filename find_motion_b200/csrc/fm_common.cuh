@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/fm_gpu.h"
 
 #define FM_MAX_K 1024          // widest supported Gaussian (taps)
@@ -75,18 +77,23 @@ struct fm_ctx {
     fm_component *comps;       // [S][Tmax][maxc]
     fm_frame_stats *stats;     // [S][Tmax]
     StreamState *state;        // [S]
-    int *errflag;              // device error word (capacity overflow)
+    int *errflag;              // device error word (capacity overflow), sticky until fm_ctx_check / fm_ctx_reset
+    int *nvalid;               // [S] frames of each stream that are real in the current call (ragged batches)
+    int *nvalid_host;          // [S] last uploaded copy (uploaded only when it changes)
     CclScratch ccl;
     int *spans;                // mask raster scratch [h][2]
     int last_T;                // frames per stream of the last call
     bool planes_valid;
-    // host staging for fm_process_host
-    uint8_t *stage_dev;
-    size_t stage_bytes;
-    fm_frame_stats *stats_pinned;
-    cudaStream_t own_stream;
-    cudaStream_t side_stream;  // contour stage of the first half of a call overlaps the second half's K1
-    cudaEvent_t ev_half[3];
+    // host entry points (fm_process_host, fm_submit_host / fm_wait): two slots, so that the host->device copy of
+    // batch i+1 runs on the copy stream while the kernels of batch i run on the compute stream
+    uint8_t *stage_dev[2];
+    size_t stage_bytes[2];
+    fm_frame_stats *stats_pinned[2];   // [S][Tmax] each
+    int slot_T[2];             // frames per stream of the batch in flight in the slot (0 = idle)
+    int *err_pinned;           // [2] error word of the slot's batch
+    cudaStream_t own_stream;   // compute
+    cudaStream_t copy_stream;  // host -> device frame copies
+    cudaEvent_t ev_copied[2], ev_done[2];
     // timing
     bool timing;               // bracket the kernel groups with events (no sync inside fm_process)
     cudaEvent_t *evs;          // [FM_TIMING_RING][4]
@@ -95,7 +102,10 @@ struct fm_ctx {
     int64_t t_calls;
 };
 
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and per function: one mutex-protected cache for
+// all kernels, so that host threads driving contexts on different (or the same) devices do not race
+int fm_ensure_smem(const void *func, size_t bytes, int device);
 void fm_set_error(const char *fmt, ...);
 
 #define FM_CUDA(call)                                                                     \
@@ -110,7 +120,7 @@ void fm_set_error(const char *fmt, ...);
 
 #define FM_LAUNCH_CHECK()                                                         \
     do {                                                                          \
-        g_launches++;                                                             \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                       \
         cudaError_t e_ = cudaGetLastError();                                      \
         if (e_ != cudaSuccess) {                                                  \
             fm_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), \
@@ -123,10 +133,8 @@ void fm_set_error(const char *fmt, ...);
 int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
                        cudaStream_t st);
 int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st);
-int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
-                    cudaStream_t st, int t0, int Th, int force_bg);
-int fm_launch_morph_begin(fm_ctx *c, int T, cudaStream_t st);
-int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st);
+int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
+int fm_ccl_configure(fm_ctx *c);
 int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_masks(fm_ctx *c, int stream, int n_polys, const int *offs, const int *pts_scaled,

@@ -2,6 +2,7 @@
 // computes it (find_motion/find_motion.py:334-335, 406, 422-423, 482-484), table
 // construction (Gaussian taps A.3, INTER_AREA taps A.1) and the C-ABI entry points of
 // include/fm_gpu.h.
+#include <ctype.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -9,12 +10,29 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
+
+#include <sched.h>
+#include <unistd.h>
 
 #include "fm_common.cuh"
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_err[512] = "";
+
+int fm_ensure_smem(const void *func, size_t bytes, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &have = done[std::make_pair(func, device)];
+    if (bytes <= have) return FM_OK;
+    FM_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return FM_OK;
+}
 
 void fm_set_error(const char *fmt, ...) {
     va_list ap;
@@ -25,7 +43,7 @@ void fm_set_error(const char *fmt, ...) {
 
 extern "C" const char *fm_last_error(void) { return g_err; }
 extern "C" int fm_version(void) { return 100; }
-extern "C" uint64_t fm_launch_count(void) { return g_launches; }
+extern "C" uint64_t fm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // --------------------------------------------------------------------------------------------
 // tables
@@ -121,6 +139,7 @@ static int upload_tab(ResizeTab *d, const HostTab &h) {
 extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
     cudaFree(c->coef); cudaFree(c->wtab);
     cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
@@ -128,13 +147,18 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
     cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
     cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
-    cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->stage_dev);
+    cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->nvalid);
+    free(c->nvalid_host);
     fm_ccl_free(&c->ccl);
-    if (c->stats_pinned) cudaFreeHost(c->stats_pinned);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->stage_dev[i]);
+        if (c->stats_pinned[i]) cudaFreeHost(c->stats_pinned[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    if (c->err_pinned) cudaFreeHost(c->err_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
-    for (int i = 0; i < 3; i++)
-        if (c->ev_half[i]) cudaEventDestroy(c->ev_half[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->evs) {
         for (int i = 0; i < 4 * FM_TIMING_RING; i++) cudaEventDestroy(c->evs[i]);
         delete[] c->evs;
@@ -192,9 +216,18 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     c->N = c->w * c->h;
     c->ntiles = (c->N + FM_TILE_PX - 1) / FM_TILE_PX;
     c->maxc = cfg->max_components > 0 ? cfg->max_components : 256;
+    inf.max_components = c->maxc;
 
     int rc = FM_OK;
     auto fail = [&](int code) { fm_ctx_destroy(c); return code; };
+#define FM_TRY(call)                                                                       \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            fm_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(FM_ECUDA);                                                         \
+        }                                                                                  \
+    } while (0)
 
     // resize mode (cv2::resize INTER_AREA dispatch)
     if (c->w == c->W && c->h == c->H) {
@@ -243,6 +276,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     {
         std::vector<int> taps = gauss_coeffs(c->k);
         if ((rc = upload(&c->coef, taps))) return fail(rc);
+        // the shared-memory needs of the wide blur are checked here, not at the first launch
         if (!c->fused && (rc = fm_wide_init(c, taps.data()))) return fail(rc);
     }
 
@@ -257,12 +291,13 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
             return fail(FM_ENOMEM);                                                       \
         }                                                                                 \
     } while (0)
-    // the fused front end never materialises gray / horizontal / blur planes (except as parity taps)
-    const bool need_planes = !c->fused || (cfg->flags & FM_FLAG_KEEP_PLANES);
-    const bool need_hor = !c->fused;
-    ALLOC(c->gray, need_planes ? F * c->N : 16);
-    ALLOC(c->hor, !need_hor ? 16 : std::max(F * c->N * sizeof(uint16_t), 2 * fm_wide_plane_bytes(c)));
-    ALLOC(c->blur, need_planes ? F * c->N + 64 : 64);
+    // the fused front ends never materialise gray / blur planes (except as parity taps)
+    const bool keep = (cfg->flags & FM_FLAG_KEEP_PLANES) != 0;
+    const bool need_gray = keep || !c->fused;
+    const bool need_blur = keep || !c->fused;
+    ALLOC(c->gray, need_gray ? F * c->N : 16);
+    ALLOC(c->hor, c->fused ? 16 : 2 * fm_wide_plane_bytes(c));
+    ALLOC(c->blur, need_blur ? F * c->N + 64 : 64);
     const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX,
                                        c->fused ? fm_fused_bg_doubles(c) : (c->wide_fused ? fm_wide_bg_doubles(c) : (size_t)0));
     ALLOC(c->bg, bg_doubles * sizeof(double));
@@ -282,12 +317,18 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     ALLOC(c->stats, F * sizeof(fm_frame_stats));
     ALLOC(c->state, (size_t)c->S * sizeof(StreamState));
     ALLOC(c->errflag, sizeof(int));
-    FM_CUDA(cudaMemset(c->maskbits, 0, (size_t)c->S * c->h * c->wpr * 4));
-    FM_CUDA(cudaMemset(c->maskflat, 0, (size_t)c->S * flatw * 4));
-    FM_CUDA(cudaMemset(c->tflat, 0, (F * flatw + FM_TILE_WORDS) * 4));
-    FM_CUDA(cudaMemset(c->bg, 0, bg_doubles * sizeof(double)));
-    FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
-    FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
+    ALLOC(c->nvalid, (size_t)c->S * sizeof(int));
+    c->nvalid_host = (int *)malloc((size_t)c->S * sizeof(int));
+    if (!c->nvalid_host) { fm_set_error("out of host memory"); return fail(FM_ENOMEM); }
+    for (int s = 0; s < c->S; s++) c->nvalid_host[s] = c->Tmax;
+    FM_TRY(cudaMemcpy(c->nvalid, c->nvalid_host, (size_t)c->S * sizeof(int), cudaMemcpyHostToDevice));
+    FM_TRY(cudaMemset(c->maskbits, 0, (size_t)c->S * c->h * c->wpr * 4));
+    FM_TRY(cudaMemset(c->maskflat, 0, (size_t)c->S * flatw * 4));
+    FM_TRY(cudaMemset(c->tflat, 0, (F * flatw + FM_TILE_WORDS) * 4));
+    FM_TRY(cudaMemset(c->bg, 0, bg_doubles * sizeof(double)));
+    FM_TRY(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
+    FM_TRY(cudaMemset(c->errflag, 0, sizeof(int)));
+    FM_TRY(cudaMemset(c->heavy, 0, F * sizeof(int)));
     // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
     // most w/4 + 2 runs of either polarity; sub-batch sized to <= 8 GB (only the slots of existing runs are ever touched)
     int cap = c->w / 4 + 3;
@@ -295,9 +336,15 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     size_t budget = (size_t)8 << 30;
     int nb = (int)std::min<size_t>(F, std::max<size_t>(1, budget / per_frame));
     if ((rc = fm_ccl_alloc(&c->ccl, nb, c->h, cap))) return fail(rc);
-    FM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    FM_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; i++) FM_CUDA(cudaEventCreateWithFlags(&c->ev_half[i], cudaEventDisableTiming));
+    if ((rc = fm_ccl_configure(c))) return fail(rc);
+    FM_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    FM_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        FM_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        FM_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+#undef FM_TRY
+#undef ALLOC
     *out = c;
     return FM_OK;
 }
@@ -313,10 +360,26 @@ extern "C" int fm_ctx_reset(fm_ctx *c, int stream) {
     if (stream >= c->S) { fm_set_error("stream %d out of range", stream); return FM_EINVAL; }
     FM_CUDA(cudaSetDevice(c->cfg.device));
     FM_CUDA(cudaDeviceSynchronize());
-    if (stream < 0)
+    if (stream < 0) {
         FM_CUDA(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
-    else
+        FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
+    } else {
         FM_CUDA(cudaMemset(c->state + stream, 0, sizeof(StreamState)));
+    }
+    return FM_OK;
+}
+
+extern "C" int fm_ctx_check(fm_ctx *c) {
+    if (!c) { fm_set_error("null context"); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaDeviceSynchronize());
+    int err = 0;
+    FM_CUDA(cudaMemcpy(&err, c->errflag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+        FM_CUDA(cudaMemset(c->errflag, 0, sizeof(int)));
+        fm_set_error("contour stage: run capacity exceeded (results of the affected frames are not valid)");
+        return FM_ERANGE;
+    }
     return FM_OK;
 }
 
@@ -325,6 +388,7 @@ extern "C" int fm_ctx_set_masks(fm_ctx *c, int stream, int n_polys, const int32_
     if (!c || n_polys < 0 || (n_polys > 0 && (!poly_offsets || !xy))) { fm_set_error("bad mask arguments"); return FM_EINVAL; }
     if (stream >= c->S) { fm_set_error("stream %d out of range", stream); return FM_EINVAL; }
     FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaDeviceSynchronize());
     int npts = n_polys ? poly_offsets[n_polys] : 0;
     std::vector<int> pts((size_t)npts * 2);
     const double scale = c->info.scale;
@@ -356,8 +420,8 @@ static int timing_drain(fm_ctx *c) {
     return FM_OK;
 }
 
-extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
-                          int n_frames, void *cuda_stream, fm_frame_stats *stats_dev) {
+extern "C" int fm_process_ragged(fm_ctx *c, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
+                                 int n_frames, const int32_t *n_valid, void *cuda_stream, fm_frame_stats *stats_dev) {
     if (!c || !frames) { fm_set_error("null argument"); return FM_EINVAL; }
     if (n_frames < 1 || n_frames > c->Tmax) {
         fm_set_error("n_frames %d outside [1, max_frames=%d]", n_frames, c->Tmax);
@@ -366,7 +430,16 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     FM_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
-    const bool fused = c->fused;
+    {   // frames of each stream that are real in this call (uploaded only when the vector changes)
+        bool changed = false;
+        for (int s = 0; s < c->S; s++) {
+            int v = n_valid ? n_valid[s] : n_frames;
+            if (v < 0 || v > n_frames) { fm_set_error("n_valid[%d] = %d outside [0, n_frames=%d]", s, v, n_frames); return FM_EINVAL; }
+            if (v != c->nvalid_host[s]) { c->nvalid_host[s] = v; changed = true; }
+        }
+        // pageable source: the runtime stages the bytes before returning, so nvalid_host may change right after
+        if (changed) FM_CUDA(cudaMemcpyAsync(c->nvalid, c->nvalid_host, (size_t)c->S * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
     {   // per-frame result slots of the call: ranges = -1 (nothing set), counters = 0
         const size_t Fmax = (size_t)c->S * c->Tmax;
         FM_CUDA(cudaMemsetAsync(c->rawrange, 0xFF, Fmax * 6 * sizeof(int), st));
@@ -378,30 +451,8 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
         ev = c->evs + 4 * c->ev_pending++;
         FM_CUDA(cudaEventRecord(ev[0], st));
     }
-    if (fused && n_frames >= 4 && (c->cfg.flags & FM_FLAG_OVERLAP)) {
-        // two halves: the dilation + contour kernels of the first half run on a side stream while K1 works
-        // on the second half; the caller's stream joins before the call returns its work to the caller
-        const int Ta = n_frames / 2, Tb = n_frames - Ta;
-        cudaStream_t sd = c->side_stream;
-        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, 0, Ta, 0))) return rc;
-        FM_CUDA(cudaEventRecord(c->ev_half[0], st));
-        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, Ta, Tb, 1))) return rc;
-        FM_CUDA(cudaEventRecord(c->ev_half[1], st));
-        if (ev) { FM_CUDA(cudaEventRecord(ev[1], st)); FM_CUDA(cudaEventRecord(ev[2], st)); }
-        FM_CUDA(cudaStreamWaitEvent(sd, c->ev_half[0], 0));
-        if ((rc = fm_launch_morph_begin(c, n_frames, sd))) return rc;
-        if ((rc = fm_launch_morph_range(c, n_frames, 0, Ta, sd))) return rc;
-        FM_CUDA(cudaStreamWaitEvent(sd, c->ev_half[1], 0));
-        if ((rc = fm_launch_morph_range(c, n_frames, Ta, Tb, sd))) return rc;
-        if ((rc = fm_launch_decide(c, n_frames, sd, stats_dev))) return rc;
-        FM_CUDA(cudaEventRecord(c->ev_half[2], sd));
-        FM_CUDA(cudaStreamWaitEvent(st, c->ev_half[2], 0));
-        if (ev) FM_CUDA(cudaEventRecord(ev[3], st));
-        c->last_T = n_frames;
-        c->planes_valid = true;
-        return FM_OK;
-    } else if (fused) {
-        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st, 0, n_frames, 0))) return rc;
+    if (c->fused) {
+        if ((rc = fm_launch_fused(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
         if (ev) { FM_CUDA(cudaEventRecord(ev[1], st)); FM_CUDA(cudaEventRecord(ev[2], st)); }
     } else {
         if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
@@ -416,45 +467,163 @@ extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride
     return FM_OK;
 }
 
-extern "C" int fm_process_host(fm_ctx *c, const uint8_t *frames_host, size_t stream_stride, size_t frame_stride,
-                               int n_frames, fm_frame_stats *stats_host) {
-    if (!c || !frames_host || !stats_host) { fm_set_error("null argument"); return FM_EINVAL; }
+extern "C" int fm_process(fm_ctx *c, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
+                          int n_frames, void *cuda_stream, fm_frame_stats *stats_dev) {
+    return fm_process_ragged(c, frames, stream_stride, frame_stride, n_frames, nullptr, cuda_stream, stats_dev);
+}
+
+// ---- host buffers: pipelined (submit / wait on two slots) and the blocking form built on it ----
+extern "C" int fm_submit_host(fm_ctx *c, int slot, const uint8_t *frames_host, size_t stream_stride, size_t frame_stride,
+                              int n_frames, const int32_t *n_valid) {
+    if (!c || !frames_host) { fm_set_error("null argument"); return FM_EINVAL; }
+    if (slot < 0 || slot > 1) { fm_set_error("slot %d outside [0, 1]", slot); return FM_EINVAL; }
     if (n_frames < 1 || n_frames > c->Tmax) {
         fm_set_error("n_frames %d outside [1, max_frames=%d]", n_frames, c->Tmax);
         return FM_EINVAL;
     }
+    if (c->slot_T[slot]) { fm_set_error("slot %d still holds a batch: call fm_wait first", slot); return FM_EINVAL; }
     FM_CUDA(cudaSetDevice(c->cfg.device));
     const size_t fb = (size_t)c->W * c->H * 3;
     const size_t need = (size_t)c->S * n_frames * fb;
-    if (c->stage_bytes < need) {
-        cudaFree(c->stage_dev);
-        c->stage_dev = nullptr; c->stage_bytes = 0;
-        FM_CUDA(cudaMalloc(&c->stage_dev, need));
-        c->stage_bytes = need;
+    if (c->stage_bytes[slot] < need) {
+        cudaFree(c->stage_dev[slot]);
+        c->stage_dev[slot] = nullptr; c->stage_bytes[slot] = 0;
+        const size_t full = (size_t)c->S * c->Tmax * fb;           // sized once for the largest batch
+        FM_CUDA(cudaMalloc(&c->stage_dev[slot], full));
+        c->stage_bytes[slot] = full;
     }
-    if (!c->stats_pinned) FM_CUDA(cudaMallocHost(&c->stats_pinned, (size_t)c->S * c->Tmax * sizeof(fm_frame_stats)));
-    cudaStream_t st = c->own_stream;
-    // densely packed device copy: [stream][frame][H][W][3]
-    if (frame_stride == fb && stream_stride == fb * (size_t)n_frames) {
-        FM_CUDA(cudaMemcpyAsync(c->stage_dev, frames_host, need, cudaMemcpyHostToDevice, st));
-    } else if (frame_stride == fb) {
-        for (int s = 0; s < c->S; s++)
-            FM_CUDA(cudaMemcpyAsync(c->stage_dev + (size_t)s * n_frames * fb, frames_host + s * stream_stride,
-                                    (size_t)n_frames * fb, cudaMemcpyHostToDevice, st));
+    if (!c->stats_pinned[slot]) FM_CUDA(cudaMallocHost(&c->stats_pinned[slot], (size_t)c->S * c->Tmax * sizeof(fm_frame_stats)));
+    if (!c->err_pinned) { FM_CUDA(cudaMallocHost(&c->err_pinned, 2 * sizeof(int))); c->err_pinned[0] = c->err_pinned[1] = 0; }
+    cudaStream_t cs = c->copy_stream, st = c->own_stream;
+    uint8_t *dev = c->stage_dev[slot];
+    // densely packed device copy [stream][frame][H][W][3]; only the real frames of a ragged batch travel.
+    // The staging buffer of this slot was last read by the kernels of the batch fm_wait(slot) already waited for.
+    bool ragged = false;
+    if (n_valid) for (int s = 0; s < c->S; s++) ragged |= n_valid[s] != n_frames;
+    if (!ragged && frame_stride == fb && stream_stride == fb * (size_t)n_frames) {
+        FM_CUDA(cudaMemcpyAsync(dev, frames_host, need, cudaMemcpyHostToDevice, cs));
     } else {
-        for (int s = 0; s < c->S; s++)
-            FM_CUDA(cudaMemcpy2DAsync(c->stage_dev + (size_t)s * n_frames * fb, fb, frames_host + s * stream_stride,
-                                      frame_stride, fb, n_frames, cudaMemcpyHostToDevice, st));
+        for (int s = 0; s < c->S; s++) {
+            const int nv = n_valid ? n_valid[s] : n_frames;
+            if (nv <= 0) continue;
+            if (frame_stride == fb)
+                FM_CUDA(cudaMemcpyAsync(dev + (size_t)s * n_frames * fb, frames_host + s * stream_stride, (size_t)nv * fb,
+                                        cudaMemcpyHostToDevice, cs));
+            else
+                FM_CUDA(cudaMemcpy2DAsync(dev + (size_t)s * n_frames * fb, fb, frames_host + s * stream_stride, frame_stride,
+                                          fb, nv, cudaMemcpyHostToDevice, cs));
+        }
     }
-    int rc = fm_process(c, c->stage_dev, fb * (size_t)n_frames, fb, n_frames, st, nullptr);
+    FM_CUDA(cudaEventRecord(c->ev_copied[slot], cs));
+    FM_CUDA(cudaStreamWaitEvent(st, c->ev_copied[slot], 0));
+    int rc = fm_process_ragged(c, dev, fb * (size_t)n_frames, fb, n_frames, n_valid, st, nullptr);
     if (rc) return rc;
     const size_t sb = (size_t)c->S * n_frames * sizeof(fm_frame_stats);
-    FM_CUDA(cudaMemcpyAsync(c->stats_pinned, c->stats, sb, cudaMemcpyDeviceToHost, st));
-    int err = 0;
-    FM_CUDA(cudaMemcpyAsync(&err, c->errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FM_CUDA(cudaStreamSynchronize(st));
-    if (err) { fm_set_error("contour stage: run capacity exceeded"); return FM_ERANGE; }
-    memcpy(stats_host, c->stats_pinned, sb);
+    FM_CUDA(cudaMemcpyAsync(c->stats_pinned[slot], c->stats, sb, cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaMemcpyAsync(c->err_pinned + slot, c->errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaEventRecord(c->ev_done[slot], st));
+    c->slot_T[slot] = n_frames;
+    return FM_OK;
+}
+
+extern "C" int fm_wait(fm_ctx *c, int slot, fm_frame_stats *stats_host) {
+    if (!c || !stats_host) { fm_set_error("null argument"); return FM_EINVAL; }
+    if (slot < 0 || slot > 1 || !c->slot_T[slot]) { fm_set_error("no batch in flight in slot %d", slot); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    const int T = c->slot_T[slot];
+    c->slot_T[slot] = 0;
+    FM_CUDA(cudaEventSynchronize(c->ev_done[slot]));
+    if (c->err_pinned[slot]) {
+        c->err_pinned[slot] = 0;
+        cudaMemsetAsync(c->errflag, 0, sizeof(int), c->own_stream);
+        fm_set_error("contour stage: run capacity exceeded");
+        return FM_ERANGE;
+    }
+    memcpy(stats_host, c->stats_pinned[slot], (size_t)c->S * T * sizeof(fm_frame_stats));
+    return FM_OK;
+}
+
+extern "C" int fm_submit_reset(fm_ctx *c, int stream) {
+    if (!c) { fm_set_error("null context"); return FM_EINVAL; }
+    if (stream < 0 || stream >= c->S) { fm_set_error("stream %d out of range", stream); return FM_EINVAL; }
+    FM_CUDA(cudaSetDevice(c->cfg.device));
+    FM_CUDA(cudaMemsetAsync(c->state + stream, 0, sizeof(StreamState), c->own_stream));
+    return FM_OK;
+}
+
+extern "C" int fm_process_host(fm_ctx *c, const uint8_t *frames_host, size_t stream_stride, size_t frame_stride,
+                               int n_frames, fm_frame_stats *stats_host) {
+    if (!c || !frames_host || !stats_host) { fm_set_error("null argument"); return FM_EINVAL; }
+    int rc = fm_submit_host(c, 0, frames_host, stream_stride, frame_stride, n_frames, nullptr);
+    if (rc) return rc;
+    return fm_wait(c, 0, stats_host);
+}
+
+// ---- pinned host memory next to the context's GPU ----
+// cudaHostAlloc places pages by the calling thread's memory policy (first touch by default), so the thread is moved to
+// the CPUs the kernel lists as local to the GPU's PCI function (/sys/bus/pci/devices/<bdf>/local_cpulist) for the
+// duration of the allocation and the first touch; on platforms that expose a single NUMA node this is a no-op.
+static bool parse_cpulist(const char *txt, cpu_set_t *set) {
+    CPU_ZERO(set);
+    bool any = false;
+    const char *p = txt;
+    while (*p) {
+        char *e;
+        long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long i = a; i <= b && i < CPU_SETSIZE; i++) { CPU_SET((int)i, set); any = true; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    return any;
+}
+
+static bool gpu_local_cpus(int device, cpu_set_t *set, int *node) {
+    char bdf[32] = "";
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) return false;
+    for (char *q = bdf; *q; q++) *q = (char)tolower(*q);
+    char path[128], buf[4096];
+    *node = -1;
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", node) != 1) *node = -1; fclose(f); }
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    bool ok = fgets(buf, sizeof(buf), f) != nullptr && parse_cpulist(buf, set);
+    fclose(f);
+    return ok;
+}
+
+extern "C" int fm_host_alloc(int device, size_t bytes, void **ptr, int *numa_node) {
+    if (!ptr || bytes == 0) { fm_set_error("bad argument"); return FM_EINVAL; }
+    *ptr = nullptr;
+    FM_CUDA(cudaSetDevice(device));
+    cpu_set_t old, local, both;
+    int node = -1;
+    bool moved = false;
+    if (sched_getaffinity(0, sizeof(old), &old) == 0 && gpu_local_cpus(device, &local, &node)) {
+        CPU_AND(&both, &old, &local);                     // stay inside the cpuset the process was given
+        if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &old)) moved = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
+    if (numa_node) *numa_node = node;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) {                               // first touch while the thread sits next to the GPU
+        volatile unsigned char *p = (volatile unsigned char *)*ptr;
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        for (size_t o = 0; o < bytes; o += page) p[o] = 0;
+    }
+    if (moved) sched_setaffinity(0, sizeof(old), &old);
+    if (e != cudaSuccess) {
+        fm_set_error("cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return FM_ENOMEM;
+    }
+    return FM_OK;
+}
+
+extern "C" int fm_host_free(void *ptr) {
+    if (ptr) FM_CUDA(cudaFreeHost(ptr));
     return FM_OK;
 }
 
@@ -470,7 +639,7 @@ extern "C" int fm_get_components(fm_ctx *c, int stream, int t, int max_n, fm_com
     int cnt = 0;
     FM_CUDA(cudaMemcpy(&cnt, c->ncomp + f, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
-    int m = std::min(cnt, c->maxc);
+    int m = std::min(cnt, c->maxc);                       // records the device kept (fm_info.max_components)
     std::vector<fm_component> v(m);
     if (m) FM_CUDA(cudaMemcpy(v.data(), c->comps + f * c->maxc, (size_t)m * sizeof(fm_component), cudaMemcpyDeviceToHost));
     std::sort(v.begin(), v.end(), [](const fm_component &a, const fm_component &b) {
@@ -484,6 +653,13 @@ extern "C" int fm_get_components(fm_ctx *c, int stream, int t, int max_n, fm_com
     return FM_OK;
 }
 
+namespace {
+struct DevBuf {           // scratch that is released on every return path
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}
+
 extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint8_t *blur, uint8_t *thresh,
                                double *bg) {
     if (!c) { fm_set_error("null context"); return FM_EINVAL; }
@@ -494,28 +670,27 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
     FM_CUDA(cudaSetDevice(c->cfg.device));
     FM_CUDA(cudaDeviceSynchronize());
     size_t f = (size_t)stream * c->last_T + t;
-    if ((gray || blur) && c->fused && !(c->cfg.flags & FM_FLAG_KEEP_PLANES)) {
-        fm_set_error("gray/blur planes are not materialised by the fused front end without FM_FLAG_KEEP_PLANES");
+    if ((gray || blur) && !(c->cfg.flags & FM_FLAG_KEEP_PLANES)) {
+        fm_set_error("gray/blur planes are only materialised with FM_FLAG_KEEP_PLANES");
         return FM_EINVAL;
     }
     if (gray) FM_CUDA(cudaMemcpy(gray, c->gray + f * c->N, c->N, cudaMemcpyDeviceToHost));
     if (blur) FM_CUDA(cudaMemcpy(blur, c->blur + f * c->N, c->N, cudaMemcpyDeviceToHost));
     if (thresh) {
-        uint8_t *d = nullptr;
-        FM_CUDA(cudaMalloc(&d, c->N));
-        int rc = fm_launch_thresh_export(c, stream, t, d, 0);
+        DevBuf d;
+        FM_CUDA(cudaMalloc(&d.p, c->N));
+        int rc = fm_launch_thresh_export(c, stream, t, (uint8_t *)d.p, 0);
         if (rc) return rc;
-        FM_CUDA(cudaMemcpy(thresh, d, c->N, cudaMemcpyDeviceToHost));
-        cudaFree(d);
+        FM_CUDA(cudaMemcpy(thresh, d.p, c->N, cudaMemcpyDeviceToHost));
     }
     if (bg) {
-        double *d = nullptr;
-        FM_CUDA(cudaMalloc(&d, (size_t)c->N * sizeof(double)));
-        int rc = c->fused ? fm_launch_bg_export_fused(c, stream, d, 0)
-                          : (c->wide_fused ? fm_launch_bg_export_wide(c, stream, d, 0) : fm_launch_bg_export(c, stream, d, 0));
+        DevBuf d;
+        FM_CUDA(cudaMalloc(&d.p, (size_t)c->N * sizeof(double)));
+        int rc = c->fused ? fm_launch_bg_export_fused(c, stream, (double *)d.p, 0)
+                          : (c->wide_fused ? fm_launch_bg_export_wide(c, stream, (double *)d.p, 0)
+                                           : fm_launch_bg_export(c, stream, (double *)d.p, 0));
         if (rc) return rc;
-        FM_CUDA(cudaMemcpy(bg, d, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
-        cudaFree(d);
+        FM_CUDA(cudaMemcpy(bg, d.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return FM_OK;
 }
@@ -523,12 +698,11 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
 extern "C" int fm_debug_mask(fm_ctx *c, int stream, uint8_t *mask) {
     if (!c || !mask || stream < 0 || stream >= c->S) { fm_set_error("bad argument"); return FM_EINVAL; }
     FM_CUDA(cudaSetDevice(c->cfg.device));
-    uint8_t *d = nullptr;
-    FM_CUDA(cudaMalloc(&d, c->N));
-    int rc = fm_launch_mask_export(c, stream, d, 0);
+    DevBuf d;
+    FM_CUDA(cudaMalloc(&d.p, c->N));
+    int rc = fm_launch_mask_export(c, stream, (uint8_t *)d.p, 0);
     if (rc) return rc;
-    FM_CUDA(cudaMemcpy(mask, d, c->N, cudaMemcpyDeviceToHost));
-    cudaFree(d);
+    FM_CUDA(cudaMemcpy(mask, d.p, c->N, cudaMemcpyDeviceToHost));
     return FM_OK;
 }
 

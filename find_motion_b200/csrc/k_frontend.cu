@@ -12,9 +12,11 @@ __device__ __forceinline__ uint32_t fm_gray(uint32_t b, uint32_t g, uint32_t r) 
 
 // identity-resize mode: one thread per 4 pixels of a frame (12 bytes in, 4 bytes out)
 __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ frames, size_t sstride,
-                                              size_t fstride, int T, int N, uint8_t *__restrict__ gray) {
+                                              size_t fstride, int T, int N, uint8_t *__restrict__ gray,
+                                              const int *__restrict__ nvalid) {
     int f = blockIdx.y;   // s*T + t
     int s = f / T, t = f - s * T;
+    if (t >= __ldg(nvalid + s)) return;       // not a real frame of this (ragged) call
     const uint8_t *src = frames + (size_t)s * sstride + (size_t)t * fstride;
     uint8_t *dst = gray + (size_t)f * N;
     int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -55,6 +57,7 @@ struct K0Params {
     const float *ywt;
     int max_ytaps;
     uint8_t *gray;
+    const int *nvalid;           // [S] real frames of each stream in this call
 };
 
 #define K0_THREADS 512
@@ -64,6 +67,7 @@ __global__ void __launch_bounds__(K0_THREADS) k_resize_gray(K0Params p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int f = blockIdx.y;
     const int s = f / p.T, t = f - s * p.T;
+    if (t >= __ldg(p.nvalid + s)) return;
     const int dy = blockIdx.x;
     const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
     const int rowbytes = p.W * 3;
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_warp(K0Params p,
     const int q = task % nq, fd = task / nq;
     const int f = fd / p.h, dy = fd - f * p.h;
     const int s = f / p.T, t = f - s * p.T;
+    if (t >= __ldg(p.nvalid + s)) return;
     const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
     unsigned char *rowbuf = smem + (size_t)warp * segpitch;
     const int rowbytes = p.W * 3;
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
     const int q = task % nq, fd = task / nq;
     const int f = fd / p.h, dy = fd - f * p.h;
     const int s = f / p.T, t = f - s * p.T;
+    if (t >= __ldg(p.nvalid + s)) return;
     const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
     unsigned char *rowbuf = smem + (size_t)warp * segpitch;
     const int rowbytes = p.W * 3;
@@ -410,58 +416,9 @@ __global__ void __launch_bounds__(32 * K0W_WARPS) k_resize_gray_g4(K0Params p, K
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// generic separable Gaussian, two passes through a u16 plane.
-// This is the fallback for wide kernels; the fused kernel (k_fused.cu) covers small k.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_hblur(const uint8_t *__restrict__ gray, uint16_t *__restrict__ hor,
-                                               const int *__restrict__ coef, int k, int w, int h) {
-    extern __shared__ int sc[];
-    for (int i = threadIdx.x; i < k; i += blockDim.x) sc[i] = coef[i];
-    __syncthreads();
-    int f = blockIdx.z, y = blockIdx.y;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
-    const uint8_t *row = gray + ((size_t)f * h + y) * w;
-    int r = k >> 1;
-    int acc = 0;
-    if (x - r >= 0 && x + r < w) {
-        const uint8_t *q = row + x - r;
-        for (int i = 0; i < k; i++) acc += sc[i] * q[i];
-    } else {
-        for (int i = 0; i < k; i++) acc += sc[i] * row[fm_reflect101(x + i - r, w)];
-    }
-    hor[((size_t)f * h + y) * w + x] = (uint16_t)acc;
-}
-
-__global__ void __launch_bounds__(256) k_vblur(const uint16_t *__restrict__ hor, uint8_t *__restrict__ blur,
-                                               const int *__restrict__ coef, int k, int w, int h, int wpr,
-                                               int T, const uint32_t *__restrict__ maskbits) {
-    extern __shared__ int sc[];
-    for (int i = threadIdx.x; i < k; i += blockDim.x) sc[i] = coef[i];
-    __syncthreads();
-    int f = blockIdx.z, y = blockIdx.y;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
-    const uint16_t *pl = hor + (size_t)f * h * w;
-    int r = k >> 1;
-    int acc = 0;
-    if (y - r >= 0 && y + r < h) {
-        const uint16_t *q = pl + (size_t)(y - r) * w + x;
-        for (int j = 0; j < k; j++) acc += sc[j] * q[(size_t)j * w];
-    } else {
-        for (int j = 0; j < k; j++) acc += sc[j] * pl[(size_t)fm_reflect101(y + j - r, h) * w + x];
-    }
-    int v = (acc + 32768) >> 16;
-    int s = f / T;
-    uint32_t m = maskbits[((size_t)s * h + y) * wpr + (x >> 5)];
-    if ((m >> (x & 31)) & 1) v = 0;
-    blur[((size_t)f * h + y) * w + x] = (uint8_t)v;
-}
-
 int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
     dim3 grid(((c->N + 3) / 4 + 255) / 256, c->S * T);
-    k_gray<<<grid, 256, 0, st>>>(frames, sstride, fstride, T, c->N, c->gray);
+    k_gray<<<grid, 256, 0, st>>>(frames, sstride, fstride, T, c->N, c->gray, c->nvalid);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -469,12 +426,9 @@ int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_
 int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T,
                        cudaStream_t st) {
     const int F = c->S * T;
-    const bool wide = c->k >= 3 && (c->w % 4) == 0;      // tensor-core blur (k_wide.cu)
-    if (c->resize_mode == 0 && wide) return fm_launch_wide_blur(c, frames, sstride, fstride, T, st);   // gray fused into pass 1
-    if (c->resize_mode == 0) {
-        int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
-        if (rc) return rc;
-    } else {
+    // every Gaussian the fused stencil does not take goes to the tensor-core blur (k_wide.cu)
+    if (c->resize_mode == 0) return fm_launch_wide_blur(c, frames, sstride, fstride, T, st);   // gray fused into pass 1
+    {
         K0Params p;
         p.frames = frames; p.sstride = sstride; p.fstride = fstride;
         p.T = T; p.W = c->W; p.H = c->H; p.w = c->w; p.h = c->h;
@@ -482,33 +436,24 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         p.xstart = c->xtab.start; p.xidx = c->xtab.idx; p.xwt = c->xtab.wt;
         p.ystart = c->ytab.start; p.yidx = c->ytab.idx; p.ywt = c->ytab.wt;
         p.max_ytaps = c->resize_mode == 1 ? c->ytab.max_taps : c->fy;
-        p.gray = c->gray;
+        p.gray = c->gray; p.nvalid = c->nvalid;
         int rowpitch = (c->W * 3 + 16 + 15) & ~15;
         if (c->resize_mode == 1) {
             // one warp per (frame, destination row, group of <= 32 destination columns)
             int nq = (c->w + 31) / 32, dxw = (c->w + nq - 1) / nq;
             int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 10) + 32 + 15) & ~15;
             size_t smemw = (size_t)K0W_WARPS * segpitch;
-            static size_t configured_w_dev[FM_MAX_DEVICES] = {0};
-            size_t &configured_w = configured_w_dev[c->cfg.device % FM_MAX_DEVICES];
-            if (smemw > configured_w) {
-                FM_CUDA(cudaFuncSetAttribute(k_resize_gray_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                configured_w = smemw;
-            }
+            int rc;
+            if ((rc = fm_ensure_smem((const void *)k_resize_gray_warp, smemw, c->cfg.device))) return rc;
             int tasks = c->h * F * nq;
             const bool aligned4 = ((((uintptr_t)frames) | sstride | fstride | ((size_t)c->W * 3)) & 3) == 0;
             if (aligned4 && c->g4w) {
-                static size_t configured_g_dev[FM_MAX_DEVICES] = {0};
-                size_t &configured_g = configured_g_dev[c->cfg.device % FM_MAX_DEVICES];
-                if (smemw > configured_g) {
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    FM_CUDA(cudaFuncSetAttribute(k_resize_gray_g4<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
-                    configured_g = smemw;
-                }
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<4, true>, smemw, c->cfg.device))) return rc;
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<4, false>, smemw, c->cfg.device))) return rc;
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<8, true>, smemw, c->cfg.device))) return rc;
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<8, false>, smemw, c->cfg.device))) return rc;
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<16, true>, smemw, c->cfg.device))) return rc;
+                if ((rc = fm_ensure_smem((const void *)k_resize_gray_g4<16, false>, smemw, c->cfg.device))) return rc;
                 K0GParams gp;
                 gp.g4start = c->g4start; gp.g4n = c->g4n; gp.g4off = c->g4off; gp.g4w = c->g4w;
                 const int blocks16 = segpitch / 16 + 1;         // upper bound of 16-byte blocks per segment
@@ -534,24 +479,12 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                 fm_set_error("resize front end needs %zu bytes of shared memory (frame too wide / ratio too large)", smem);
                 return FM_ERANGE;
             }
-            static size_t configured_dev[FM_MAX_DEVICES] = {0};
-            size_t &configured = configured_dev[c->cfg.device % FM_MAX_DEVICES];
-            if (smem > configured) {
-                FM_CUDA(cudaFuncSetAttribute(k_resize_gray, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
+            int rc;
+            if ((rc = fm_ensure_smem((const void *)k_resize_gray, smem, c->cfg.device))) return rc;
             dim3 grid(c->h, F);
             k_resize_gray<<<grid, K0_THREADS, smem, st>>>(p);
             FM_LAUNCH_CHECK();
         }
     }
-    // separable blur
-    if (wide) return fm_launch_wide_blur(c, nullptr, 0, 0, T, st);
-    dim3 bgrid((c->w + 255) / 256, c->h, F);
-    size_t sm = (size_t)c->k * sizeof(int);
-    k_hblur<<<bgrid, 256, sm, st>>>(c->gray, c->hor, c->coef, c->k, c->w, c->h);
-    FM_LAUNCH_CHECK();
-    k_vblur<<<bgrid, 256, sm, st>>>(c->hor, c->blur, c->coef, c->k, c->w, c->h, c->wpr, T, c->maskbits);
-    FM_LAUNCH_CHECK();
-    return FM_OK;
+    return fm_launch_wide_blur(c, nullptr, 0, 0, T, st);
 }

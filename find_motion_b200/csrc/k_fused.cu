@@ -67,9 +67,8 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
 }
 
 struct FusedParams {
-    int T, w, h, wpr;           // T = frames processed by this launch
-    int t0, Ttot;               // they are frames t0 .. t0+T-1 of a Ttot-frame call (per-stream arrays have stride Ttot)
-    int force_bg;               // the background is valid whatever the stream state says (second half of a call)
+    int T, w, h, wpr;           // T = frames per stream of the call
+    const int *nvalid;          // [S] real frames of each stream in this call (ragged batches), <= T
     int tilesX, tilesY;
     double *bg;                 // [S][tiles][8 warps][FT_RPT rows][2 pairs][32 lanes] double2
     const uint32_t *maskbits;   // [S][h][wpr]
@@ -223,7 +222,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     const int x0 = tx * FT_W, y0 = ty * FT_H;
     const int w = p.w, h = p.h;
     const bool border = (x0 == 0) || (x0 + FT_W >= w) || (y0 == 0) || (y0 + FT_H >= h);
-    const bool has_bg = p.force_bg || p.state[s].has_bg != 0;
+    const bool has_bg = p.state[s].has_bg != 0;
+    const int Ts = min(p.T, __ldg(p.nvalid + s));            // frames of this stream that are real
+    if (Ts <= 0) return;
 
     // this thread's pixels: columns x0 + 4*lane .. +3, rows y0 + FT_RPT*warp .. +FT_RPT-1
     const int px = x0 + 4 * lane, py = y0 + FT_RPT * warp;
@@ -261,9 +262,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bars[0], RAW_BYTES);
-        tma_load_4d(raw, &tmap, &bars[0], cx, cy, p.t0, s);
+        tma_load_4d(raw, &tmap, &bars[0], cx, cy, 0, s);
     }
-    uint32_t *tw = p.tbits + ((size_t)s * p.Ttot + p.t0) * p.flatwords;
+    uint32_t *tw = p.tbits + ((size_t)s * p.T) * p.flatwords;
     // B fragments of the horizontal pass (constant): the banded tap matrix for the two 8-column output blocks
     // of a 32-byte window.  Output column n of block nb is gray byte 4 + 16 j + 8 nb + n of its row, window
     // byte k is gray byte 16 j + k, so the tap index is k - n - 8 nb - 2 (taps b0 b1 b2 b1 b0).
@@ -290,12 +291,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * warp + (lane & 3);
 
     uint32_t pend = 0;
-    for (int t = 0; t < p.T; t++) {
+    for (int t = 0; t < Ts; t++) {
         // No barrier here: every thread that gets this far has passed the second barrier of frame t-1, i.e. all
         // conversions out of raw stage (t+1)&1 (frame t-1) and all reads of the gray plane are complete.
-        if (tid == 0 && t + 1 < p.T) {
+        if (tid == 0 && t + 1 < Ts) {
             mbar_expect_tx(&bars[(t + 1) & 1], RAW_BYTES);
-            tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, p.t0 + t + 1, s);
+            tma_load_4d(raw + ((t + 1) & 1) * RAW_STAGE, &tmap, &bars[(t + 1) & 1], cx, cy, t + 1, s);
         }
         mbar_wait(&bars[t & 1], (t >> 1) & 1);
         // ---- staged BGR -> gray bytes in shared memory (tile + halo) ----
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
                 int ry = u / (FT_W / 4), ux = u - ry * (FT_W / 4);
                 int gy = y0 + ry, gx = x0 + 4 * ux;
                 if (gy < h && gx < w)
-                    *reinterpret_cast<uint32_t *>(p.gray_out + (((size_t)s * p.Ttot + p.t0 + t) * h + gy) * w + gx) =
+                    *reinterpret_cast<uint32_t *>(p.gray_out + (((size_t)s * p.T + t) * h + gy) * w + gx) =
                         sg[(ry + 2) * FG_WORDS + ux + 1];
             }
         }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         __syncthreads();
         // ---- vertical pass on packed pairs, sliding 5-row window, then the temporal update ----
         const uint32_t *sgw = sh + (FT_RPT * warp) * FH_WORDS + 2 * lane;
-        uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.Ttot + p.t0 + t) * h + py) * w + px : nullptr;
+        uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.T + t) * h + py) * w + px : nullptr;
         const bool okx = px < w;
         uint32_t bits;
         if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         // ---- 8 lanes x FT_RPT rows of nibbles -> one 32-pixel word per lane, coalesced store ----
 #if FT_RPT == 4
         // a thread has 4 rows: two frames share one transpose (rows 0-3 = frame t-1, rows 4-7 = frame t)
-        if (!(t & 1) && t + 1 < p.T) {
+        if (!(t & 1) && t + 1 < Ts) {
             pend = bits;
         } else {
             const bool two = t & 1;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         }
 #endif
         if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's FT_RPT rows hold something
-            int *rr = p.rawrange + 2 * ((size_t)s * p.Ttot + p.t0 + t);
+            int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
             atomicMax(rr, min(py + FT_RPT - 1, h - 1));
             atomicMax(rr + 1, h - 1 - py);
         }
@@ -445,8 +446,7 @@ static PFN_encodeTiled get_encode() {
 
 #define FUSED_SMEM (2 * RAW_STAGE + FH_ROWS * FG_WORDS * 4 + FH_ROWS * FH_WORDS * 4 + 16)
 
-int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st, int t0,
-                    int Th, int force_bg) {
+int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
     if ((((uintptr_t)frames) & 15) || (sstride & 15) || (fstride & 15)) {
         fm_set_error("fused front end needs 16-byte aligned frames and strides (TMA)");
         return FM_EINVAL;
@@ -464,7 +464,7 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fm_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FM_ECUDA; }
     FusedParams p;
-    p.T = Th; p.t0 = t0; p.Ttot = T; p.force_bg = force_bg;
+    p.T = T; p.nvalid = c->nvalid;
     p.w = c->w; p.h = c->h; p.wpr = c->wpr;
     p.tilesX = (c->w + FT_W - 1) / FT_W; p.tilesY = (c->h + FT_H - 1) / FT_H;
     p.bg = c->bg; p.maskbits = c->maskbits; p.tbits = c->tflat;
@@ -485,15 +485,11 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
     const bool keep = (c->cfg.flags & FM_FLAG_KEEP_PLANES) != 0;
     const bool safe = p.alpha >= 0.0 && p.alpha <= 1.0 && p.threshold >= 0;
     dim3 grid(p.tilesX * p.tilesY, c->S);
-    static bool configured_dev[FM_MAX_DEVICES] = {false};
-    bool &configured = configured_dev[c->cfg.device % FM_MAX_DEVICES];
-    if (!configured) {
-        FM_CUDA(cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        FM_CUDA(cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        FM_CUDA(cudaFuncSetAttribute(k_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        FM_CUDA(cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        configured = true;
-    }
+    int rc;
+    if ((rc = fm_ensure_smem((const void *)k_fused<true, true>, FUSED_SMEM, c->cfg.device))) return rc;
+    if ((rc = fm_ensure_smem((const void *)k_fused<true, false>, FUSED_SMEM, c->cfg.device))) return rc;
+    if ((rc = fm_ensure_smem((const void *)k_fused<false, true>, FUSED_SMEM, c->cfg.device))) return rc;
+    if ((rc = fm_ensure_smem((const void *)k_fused<false, false>, FUSED_SMEM, c->cfg.device))) return rc;
     if (keep) {
         if (safe) k_fused<true, true><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);
         else k_fused<true, false><<<grid, FUSED_THREADS, FUSED_SMEM, st>>>(tmap, p);

@@ -757,11 +757,18 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
 __global__ void k_decide(StreamState *__restrict__ state, const int *__restrict__ ncomp,
                          const int *__restrict__ ncounted, fm_frame_stats *__restrict__ stats,
                          fm_frame_stats *__restrict__ stats_out, int S, int T, int cache_frames,
-                         int min_movement_frames) {
+                         int min_movement_frames, const int *__restrict__ nvalid) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     StreamState st = state[s];
-    for (int t = 0; t < T; t++) {
+    const int Ts = min(T, nvalid[s]);           // real frames of this stream in the call (ragged batches)
+    for (int t = Ts; t < T; t++) {
+        fm_frame_stats z = {0, 0, 0, 0, 0, 0, 0, 0};
+        stats[s * T + t] = z;
+        if (stats_out) stats_out[s * T + t] = z;
+    }
+    if (Ts <= 0) return;                        // the stream did not take part: state untouched
+    for (int t = 0; t < Ts; t++) {
         int f = s * T + t;
         fm_frame_stats r;
         r.n_contours = ncomp[f];
@@ -855,6 +862,26 @@ void fm_ccl_free(CclScratch *s) {
     s->xs = s->xe = nullptr; s->rowcnt = s->parent = s->area2 = s->bbox = nullptr;
 }
 
+// Shared-memory budget of k_ccl_frame_smem: the run tables (16 B per row + 80 KB) plus a row cache.  Planes that are
+// too tall for the tables (or wider than 4096 px) are labelled by the global-memory kernel alone.
+static bool ccl_smem_plan(int h, int wpr, size_t *smem, int *cache_words) {
+    const size_t tables = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
+                          (size_t)6 * CCL2_CAP * sizeof(uint16_t);
+    const size_t budget = 200 * 1024;
+    if (wpr > 128 || tables + 4096 > budget) return false;
+    const size_t room = budget - tables;                                           // shared-memory row cache
+    *smem = tables + (room < 128 * 1024 ? room : 128 * 1024);
+    *cache_words = (int)((*smem - tables) / 4);
+    return true;
+}
+
+int fm_ccl_configure(fm_ctx *c) {          // fm_ctx_create: fail here, not at the first call
+    size_t smem = 0;
+    int cw = 0;
+    if (!ccl_smem_plan(c->h, c->wpr, &smem, &cw)) return FM_OK;
+    return fm_ensure_smem((const void *)k_ccl_frame_smem, smem, c->cfg.device);
+}
+
 // labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
 static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
@@ -872,20 +899,12 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.bbox = sc.bbox; a.errflag = errflag;
         a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
         a.min_area = min_area; a.max_area = max_area;
-        if (wpr <= 128 && heavy) {
-            const size_t tables = (size_t)2 * h * sizeof(int2) + (size_t)2 * (CCL2_CAP + 2) * sizeof(int) +
-                                  (size_t)6 * CCL2_CAP * sizeof(uint16_t);
-            const size_t room = tables < 200 * 1024 ? 200 * 1024 - tables : 0;       // shared-memory row cache
-            const size_t smem = tables + (room < 128 * 1024 ? room : 128 * 1024);
-            a.cache_words = (int)((smem - tables) / 4);
-            static size_t configured_dev[FM_MAX_DEVICES] = {0};
+        size_t smem = 0;
+        if (heavy && ccl_smem_plan(h, wpr, &smem, &a.cache_words)) {
             int dev = 0;
-            cudaGetDevice(&dev);
-            size_t &configured = configured_dev[dev % FM_MAX_DEVICES];
-            if (smem > configured) {
-                FM_CUDA(cudaFuncSetAttribute(k_ccl_frame_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
+            FM_CUDA(cudaGetDevice(&dev));
+            int rc = fm_ensure_smem((const void *)k_ccl_frame_smem, smem, dev);
+            if (rc) return rc;
             k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
@@ -899,15 +918,17 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
     return FM_OK;
 }
 
-// the per-frame result slots of a call (ranges, counts) are cleared by fm_process before the front end runs
-int fm_launch_morph_begin(fm_ctx *, int, cudaStream_t) { return FM_OK; }
-
-// dilation + contours of frames [t0, t0+Th) of every stream of a T-frame call
-int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st) {
+// dilation + contours of every frame of a T-frame call (the per-frame result slots -- ranges, counts -- are cleared
+// by fm_process before the front end runs; frames beyond a stream's n_valid keep an empty range and are skipped)
+static int fm_launch_morph_range(fm_ctx *c, int T, cudaStream_t st) {
+    const int t0 = 0, Th = T;
     const int F = c->S * Th;
+    size_t smem_plan = 0;
+    int cw_plan = 0;
+    const bool smem_ok = ccl_smem_plan(c->h, c->wpr, &smem_plan, &cw_plan);
     // With enough frames to fill the GPU (one CTA per frame) the shared-memory labelling kernel dilates the raw
     // threshold bits of its frame itself; with few frames the grid-wide k_dilate (one warp per row) is faster.
-    if (c->wpr <= 128 && F >= 32)
+    if (smem_ok && F >= 32)
         return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
                        c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st, c->tflat,
                        c->rawrange, c->ntiles * FM_TILE_WORDS);
@@ -925,53 +946,60 @@ int fm_launch_morph_range(fm_ctx *c, int T, int t0, int Th, cudaStream_t st) {
 
 int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
     k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(c->state, c->ncomp, c->ncounted, c->stats, stats_out, c->S, T,
-                                                 c->info.cache_frames, c->info.min_movement_frames);
+                                                 c->info.cache_frames, c->info.min_movement_frames, c->nvalid);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
 
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
     int rc;
-    if ((rc = fm_launch_morph_begin(c, T, st))) return rc;
-    if ((rc = fm_launch_morph_range(c, T, 0, T, st))) return rc;
+    if ((rc = fm_launch_morph_range(c, T, st))) return rc;
     return fm_launch_decide(c, T, st, stats_out);
 }
 
 // standalone labelling of one host plane (parity tests of the contour stage)
-int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out, int *n) {
-    FM_CUDA(cudaSetDevice(device));
-    int wpr = (w + 31) / 32;
+namespace {
+struct PlaneScratch {                       // released on every return path
     CclScratch sc{};
-    int rc = fm_ccl_alloc(&sc, 1, h, w / 2 + 2);
-    if (rc) return rc;
     uint8_t *d8 = nullptr;
     uint32_t *pl = nullptr, *fill = nullptr;
     int *cnt = nullptr;
     fm_component *comps = nullptr;
-    int maxc = max_n > 0 ? max_n : 1;
-    FM_CUDA(cudaMalloc(&d8, (size_t)w * h));
-    FM_CUDA(cudaMalloc(&pl, (size_t)wpr * h * 4));
-    FM_CUDA(cudaMalloc(&fill, (size_t)wpr * h * 4));
-    FM_CUDA(cudaMalloc(&cnt, 4 * sizeof(int)));
-    FM_CUDA(cudaMalloc(&comps, (size_t)maxc * sizeof(fm_component)));
-    FM_CUDA(cudaMemcpy(d8, plane_host, (size_t)w * h, cudaMemcpyHostToDevice));
-    FM_CUDA(cudaMemset(cnt, 0, 4 * sizeof(int)));
-    dim3 grid((wpr + 63) / 64, h);
-    k_u8_to_bits<<<grid, 64>>>(d8, pl, w, h, wpr);
-    FM_LAUNCH_CHECK();
-    rc = ccl_run(sc, pl, fill, nullptr, 1, w, h, wpr, cnt, cnt + 1, comps, maxc, 0, 0, cnt + 2, cnt + 3, 1, 0, 1, 0);
-    FM_CUDA(cudaDeviceSynchronize());
+    ~PlaneScratch() {
+        cudaFree(d8); cudaFree(pl); cudaFree(fill); cudaFree(cnt); cudaFree(comps);
+        fm_ccl_free(&sc);
+    }
+};
+}
+
+int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out, int *n) {
+    FM_CUDA(cudaSetDevice(device));
+    int wpr = (w + 31) / 32;
+    PlaneScratch q;
+    int rc = fm_ccl_alloc(&q.sc, 1, h, w / 2 + 2);
     if (rc) return rc;
+    int maxc = max_n > 0 ? max_n : 1;
+    FM_CUDA(cudaMalloc(&q.d8, (size_t)w * h));
+    FM_CUDA(cudaMalloc(&q.pl, (size_t)wpr * h * 4));
+    FM_CUDA(cudaMalloc(&q.fill, (size_t)wpr * h * 4));
+    FM_CUDA(cudaMalloc(&q.cnt, 4 * sizeof(int)));
+    FM_CUDA(cudaMalloc(&q.comps, (size_t)maxc * sizeof(fm_component)));
+    FM_CUDA(cudaMemcpy(q.d8, plane_host, (size_t)w * h, cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMemset(q.cnt, 0, 4 * sizeof(int)));
+    dim3 grid((wpr + 63) / 64, h);
+    k_u8_to_bits<<<grid, 64>>>(q.d8, q.pl, w, h, wpr);
+    FM_LAUNCH_CHECK();
+    rc = ccl_run(q.sc, q.pl, q.fill, nullptr, 1, w, h, wpr, q.cnt, q.cnt + 1, q.comps, maxc, 0, 0, q.cnt + 2, q.cnt + 3, 1, 0, 1, 0);
+    if (rc) return rc;
+    FM_CUDA(cudaDeviceSynchronize());
     int hc[3];
-    FM_CUDA(cudaMemcpy(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+    FM_CUDA(cudaMemcpy(hc, q.cnt, sizeof(hc), cudaMemcpyDeviceToHost));
     if (hc[2]) {
         fm_set_error("contour stage: run capacity exceeded");
         return FM_ERANGE;
     }
     *n = hc[0];
     int m = hc[0] < maxc ? hc[0] : maxc;
-    if (max_n > 0 && m > 0) FM_CUDA(cudaMemcpy(out, comps, (size_t)m * sizeof(fm_component), cudaMemcpyDeviceToHost));
-    cudaFree(d8); cudaFree(pl); cudaFree(fill); cudaFree(cnt); cudaFree(comps);
-    fm_ccl_free(&sc);
+    if (max_n > 0 && m > 0) FM_CUDA(cudaMemcpy(out, q.comps, (size_t)m * sizeof(fm_component), cudaMemcpyDeviceToHost));
     return FM_OK;
 }

@@ -61,8 +61,11 @@ template <bool SAFE>
 __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ blur, double *__restrict__ bg,
                                                   uint32_t *__restrict__ tflat, const StreamState *__restrict__ state,
                                                   int T, int N, int ntiles, int threshold, double alpha,
-                                                  double beta, int *__restrict__ rawrange, int w, int h) {
+                                                  double beta, int *__restrict__ rawrange, int w, int h,
+                                                  const int *__restrict__ nframes) {
     const int s = blockIdx.y;
+    const int Ts = min(T, __ldg(nframes + s));              // real frames of this stream in the call (ragged batches)
+    if (Ts <= 0) return;
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ntiles) return;
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(256) k_temporal(const uint8_t *__restrict__ bl
     uint32_t *tw = tflat + ((size_t)s * T) * ((size_t)ntiles * FM_TILE_WORDS) + tile * FM_TILE_WORDS + (lane >> 1);
     const bool vec = (nvalid == 16) && ((((uintptr_t)bl) & 15) == 0) && ((N & 15) == 0);
 
-    for (int t = 0; t < T; t++) {
+    for (int t = 0; t < Ts; t++) {
         uint32_t px[4] = {0, 0, 0, 0};
         if (vec) {
             uint4 v = __ldg(reinterpret_cast<const uint4 *>(bl));
@@ -131,9 +134,9 @@ int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st) {
     dim3 grid((c->ntiles + 7) / 8, c->S);
     const bool safe = alpha >= 0.0 && alpha <= 1.0 && c->cfg.threshold >= 0;
     if (safe) k_temporal<true><<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
-                                                     alpha, beta, c->rawrange, c->w, c->h);
+                                                     alpha, beta, c->rawrange, c->w, c->h, c->nvalid);
     else k_temporal<false><<<grid, 256, 0, st>>>(c->blur, c->bg, c->tflat, c->state, T, c->N, c->ntiles, c->cfg.threshold,
-                                                 alpha, beta, c->rawrange, c->w, c->h);
+                                                 alpha, beta, c->rawrange, c->w, c->h, c->nvalid);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }

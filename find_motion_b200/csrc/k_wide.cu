@@ -28,6 +28,7 @@
 #define WV_ROWS 128        // pass 2 CTA tile: 128 output rows x 32 columns per step, 4 warps of 32 x 32
 #define WV_COLS 32
 #define WV_NT 4            // column tiles per pass-2 CTA (cp.async double buffer)
+#define WT_COLS 16         // columns of a k_wide_vt CTA
 
 __device__ __forceinline__ uint32_t wsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void wldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -86,6 +87,16 @@ size_t fm_wide_plane_bytes(const fm_ctx *c) {
 //   registers a0..a3 = (m = g, g+8, g, g+8; k = 4t+i, 4t+i, 16+4t+i, 16+4t+i), tap 16 (e - 1) + row(k) - m.
 int fm_wide_init(fm_ctx *c, const int *taps) {
     WideGeom g = wide_geom(c);
+    {   // shared-memory needs of the three kernels, checked when the context is created
+        const size_t smh = (size_t)32 * g.pitch + (size_t)(4 * g.Sh + 3) * 256;
+        const size_t smv = (size_t)4 * (4 + g.Sv - 1) * 2 * WV_COLS * 16 + (size_t)2 * g.Sv * 512;
+        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512;
+        if (smh > 200 * 1024 || smv > 200 * 1024 || smt > 200 * 1024) {
+            fm_set_error("Gaussian kernel %d too wide for the tensor-core blur (%zu / %zu / %zu bytes of shared memory)", c->k,
+                         smh, smv, smt);
+            return FM_ERANGE;
+        }
+    }
     const int nh = 4 * g.Sh + 3, nv = 2 * g.Sv;
     const size_t words = (size_t)nh * 32 * 2 + (size_t)nv * 32 * 4;
     uint32_t *hh = (uint32_t *)malloc(words * 4);
@@ -146,12 +157,13 @@ template <bool BGR>
 __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
                                                        uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
                                                        const uint2 *__restrict__ tabg, int w, int h, int r, int R16, int Sh,
-                                                       int pitch, int NGa) {
+                                                       int pitch, int NGa, const int *__restrict__ nvalid) {
     extern __shared__ __align__(16) unsigned char wsm[];
     unsigned char *tile = wsm;                                              // [32][pitch] gray bytes
     uint2 *tab = reinterpret_cast<uint2 *>(wsm + 32 * pitch);             // [4 Sh + 3][32]
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
+    if (f % T >= __ldg(nvalid + f / T)) return;                             // not a real frame of this (ragged) call
     for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
     // stage the window: shared column cc <-> image column X0 - R16 + cc (reflected), row rr <-> padded row 32 G + rr
     if (BGR) {
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restr
                 const int x = X0 - R16 + 4 * cw;
                 if (x >= min(X0 + WH_COLS, w) + r) break;
                 uint32_t v;
-                if (x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+                if (x >= 0 && x + 3 < w && (((uintptr_t)(row + x)) & 3) == 0) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
                 else {
                     v = 0;
 #pragma unroll
@@ -273,8 +285,10 @@ __device__ __forceinline__ int wv_slot(int c) { return (c & 24) | ((c & 7) ^ (((
 // dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 32 columns * 16 B  +  2 Sv * 512
 __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo, const uint4 *__restrict__ phi,
                                                 uint8_t *__restrict__ blur, const uint4 *__restrict__ tabg, int w, int h,
-                                                int Sv, int NGa, int wpr, int T, const uint32_t *__restrict__ maskbits) {
+                                                int Sv, int NGa, int wpr, int T, const uint32_t *__restrict__ maskbits,
+                                                const int *__restrict__ nvalid) {
     extern __shared__ __align__(16) unsigned char wsm[];
+    if ((int)blockIdx.z % T >= __ldg(nvalid + blockIdx.z / T)) return;      // not a real frame of this (ragged) call
     const int NGt = 4 + Sv - 1;
     const int per = NGt * 2 * WV_COLS;                                        // 16-byte chunks per plane and stage
     uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][32 slots]
@@ -372,8 +386,16 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
                     const uint32_t m = __ldg(mp + dy * wpr) >> (8 * t);
                     uint8_t *dst = dp0 + dy * w;
                     // masked pixels -> 0xFF bytes -> cleared
-                    if (ok0) *reinterpret_cast<uint32_t *>(dst) = wd[0] & ~((((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
-                    if (ok1) *reinterpret_cast<uint32_t *>(dst + 4) = wd[1] & ~(((((m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                    const uint32_t o0 = wd[0] & ~((((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                    const uint32_t o1 = wd[1] & ~(((((m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                    if ((w & 3) == 0) {
+                        if (ok0) *reinterpret_cast<uint32_t *>(dst) = o0;
+                        if (ok1) *reinterpret_cast<uint32_t *>(dst + 4) = o1;
+                    } else {                      // rows are not word aligned: guarded byte stores
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            if (X0 + 8 * t + b < w) dst[b] = (uint8_t)((b < 4 ? o0 : o1) >> (8 * (b & 3)));
+                    }
                 }
             }
         __syncthreads();       // every warp is done with this stage before the loads of tile ct + 2 overwrite it
@@ -387,8 +409,6 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
 // pixels whose float64 background stays in registers for all T frames (find_motion.py:246-257, 651-659).
 // Background layout: [S][tilesY][tilesX][warp 4][8][lane 32] double2 (thread-private, coalesced).
 // ---------------------------------------------------------------------------------------------
-#define WT_COLS 16
-
 // shared slot of column c of a 16-column tile: the 8 columns {4t' + 2nb + e} of a block land in 8 different 16-byte lanes
 __device__ __forceinline__ int wt_slot(int c) { return c ^ ((c >> 3) << 1); }
 
@@ -399,6 +419,7 @@ struct WideVtParams {
     uint32_t *tbits;            // [S][T][flatwords] raw threshold bits (flat order == row-padded order since w % 32 == 0)
     const uint32_t *maskbits;   // [S][h][wpr]
     const StreamState *state;
+    const int *nvalid;          // [S] real frames of each stream in this call
     int *rawrange;              // [S][T][2]
     uint8_t *blur_out;          // [S][T][h][w] parity tap (KEEP) or null
     int w, h, Sv, NGa, wpr, T, threshold, tilesX, tilesY;
@@ -434,6 +455,8 @@ __device__ __forceinline__ uint32_t wt_temporal4(const int (&lo)[4], const int (
 __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int Sv = p.Sv, w = p.w, h = p.h, NGa = p.NGa, T = p.T;
+    const int Ts = min(T, __ldg(p.nvalid + blockIdx.z));                      // real frames of this stream (ragged batches)
+    if (Ts <= 0) return;
     const int NGt = 4 + Sv - 1;
     const int per = NGt * 2 * WT_COLS;                                        // 16-byte chunks per plane and stage
     uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][16 slots]
@@ -495,8 +518,8 @@ __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
     const uint32_t nthr2 = ~(2u * (uint32_t)p.threshold);
     const double nC = -(4503599627370496.0 * p.alpha);
     uint16_t *tw = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * T * p.flatwords) + (size_t)2 * (X0 >> 5) + ((X0 >> 4) & 1);
-    for (int t = 0; t < T; t++) {
-        if (t + 1 < T) {
+    for (int t = 0; t < Ts; t++) {
+        if (t + 1 < Ts) {
             issue(t + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
@@ -601,18 +624,10 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
     const uint4 *tabv = reinterpret_cast<const uint4 *>(c->wtab + (size_t)(4 * g.Sh + 3) * 32 * 2);
     const size_t smh = (size_t)32 * g.pitch + (size_t)(4 * g.Sh + 3) * 256;
     const size_t smv = (size_t)4 * (4 + g.Sv - 1) * 2 * WV_COLS * 16 + (size_t)2 * g.Sv * 512;
-    if (smh > 200 * 1024 || smv > 200 * 1024) {
-        fm_set_error("Gaussian kernel %d too wide for the tensor-core blur (%zu / %zu bytes of shared memory)", c->k, smh, smv);
-        return FM_ERANGE;
-    }
-    static size_t conf_h[FM_MAX_DEVICES] = {0}, conf_v[FM_MAX_DEVICES] = {0};
-    size_t &ch = conf_h[c->cfg.device % FM_MAX_DEVICES], &cv = conf_v[c->cfg.device % FM_MAX_DEVICES];
-    if (smh > ch) {
-        FM_CUDA(cudaFuncSetAttribute(k_wide_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
-        FM_CUDA(cudaFuncSetAttribute(k_wide_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smh));
-        ch = smh;
-    }
-    if (smv > cv) { FM_CUDA(cudaFuncSetAttribute(k_wide_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv)); cv = smv; }
+    int rc;
+    if ((rc = fm_ensure_smem((const void *)k_wide_h<true>, smh, c->cfg.device))) return rc;
+    if ((rc = fm_ensure_smem((const void *)k_wide_h<false>, smh, c->cfg.device))) return rc;
+    if ((rc = fm_ensure_smem((const void *)k_wide_v, smv, c->cfg.device))) return rc;
     dim3 hgrid((c->w + WH_COLS - 1) / WH_COLS, g.NGa, F);
     const bool aligned16 = frames && ((((uintptr_t)frames) | sstride | fstride | ((size_t)c->w * 3)) & 15) == 0;
     if (aligned16) {
@@ -621,24 +636,23 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
             if (rc) return rc;
         }
         k_wide_h<true><<<hgrid, WH_THREADS, smh, st>>>(frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
-                                                       g.Sh, g.pitch, g.NGa);
+                                                       g.Sh, g.pitch, g.NGa, c->nvalid);
     } else {
         if (frames) {
             int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
             if (rc) return rc;
         }
         k_wide_h<false><<<hgrid, WH_THREADS, smh, st>>>(c->gray, 0, 0, T, plo, phi, tabh, c->w, c->h, g.r, g.R16, g.Sh,
-                                                        g.pitch, g.NGa);
+                                                        g.pitch, g.NGa, c->nvalid);
     }
     FM_LAUNCH_CHECK();
     if (c->wide_fused) {
         const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512;
-        static size_t conf_t[FM_MAX_DEVICES] = {0};
-        size_t &ct = conf_t[c->cfg.device % FM_MAX_DEVICES];
-        if (smt > ct) { FM_CUDA(cudaFuncSetAttribute(k_wide_vt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt)); ct = smt; }
+        if ((rc = fm_ensure_smem((const void *)k_wide_vt, smt, c->cfg.device))) return rc;
         WideVtParams p;
         p.plo = reinterpret_cast<const uint4 *>(plo); p.phi = reinterpret_cast<const uint4 *>(phi); p.tabg = tabv;
         p.bg = c->bg; p.tbits = c->tflat; p.maskbits = c->maskbits; p.state = c->state; p.rawrange = c->rawrange;
+        p.nvalid = c->nvalid;
         p.blur_out = (c->cfg.flags & FM_FLAG_KEEP_PLANES) ? c->blur : nullptr;
         p.w = c->w; p.h = c->h; p.Sv = g.Sv; p.NGa = g.NGa; p.wpr = c->wpr; p.T = T; p.threshold = c->cfg.threshold;
         p.tilesX = (c->w + WT_COLS - 1) / WT_COLS; p.tilesY = (c->h + WV_ROWS - 1) / WV_ROWS;
@@ -651,7 +665,7 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
     }
     dim3 vgrid((c->w + WV_COLS * WV_NT - 1) / (WV_COLS * WV_NT), (c->h + WV_ROWS - 1) / WV_ROWS, F);
     k_wide_v<<<vgrid, 128, smv, st>>>(reinterpret_cast<const uint4 *>(plo), reinterpret_cast<const uint4 *>(phi), c->blur,
-                                      tabv, c->w, c->h, g.Sv, g.NGa, c->wpr, T, c->maskbits);
+                                      tabv, c->w, c->h, g.Sv, g.NGa, c->wpr, T, c->maskbits, c->nvalid);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }

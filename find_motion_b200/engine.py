@@ -19,7 +19,7 @@ STATS_DTYPE = np.dtype([(n, np.int32) for n in ("n_contours", "n_counted", "move
 class MotionEngine:
     def __init__(self, frame_width, frame_height, n_streams=1, max_frames=8, device=0, fps=30, box_size=100,
                  min_box_scale=50, cache_time=2.0, min_time=0.5, threshold=7, avg=0.1, blur_scale=20,
-                 mask_areas=None, max_components=256, keep_planes=False, no_fused=False, overlap=False):
+                 mask_areas=None, max_components=256, keep_planes=False, no_fused=False):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         cfg = _lib.fm_config(
@@ -27,17 +27,18 @@ class MotionEngine:
             max_frames=max_frames, fps=int(fps), box_size=int(box_size), min_box_scale=int(min_box_scale),
             blur_scale=int(blur_scale), threshold=int(threshold), avg=float(avg), min_time=float(min_time),
             cache_time=float(cache_time), max_components=max_components,
-            flags=(_lib.FLAG_KEEP_PLANES if keep_planes else 0) | (_lib.FLAG_NO_FUSED if no_fused else 0) |
-            (_lib.FLAG_OVERLAP if overlap else 0))
+            flags=(_lib.FLAG_KEEP_PLANES if keep_planes else 0) | (_lib.FLAG_NO_FUSED if no_fused else 0))
         _lib.check(self._lib.fm_ctx_create(C.byref(cfg), C.byref(self._ctx)))
         self.device = device
         self.n_streams, self.max_frames = n_streams, max_frames
         self.W, self.H = frame_width, frame_height
         inf = _lib.fm_info()
         _lib.check(self._lib.fm_ctx_info(self._ctx, C.byref(inf)))
-        self.info = {f: getattr(inf, f) for f, _ in _lib.fm_info._fields_ if f != "reserved"}
+        self.info = {f: getattr(inf, f) for f, _ in _lib.fm_info._fields_}
         self.w, self.h = inf.proc_width, inf.proc_height
+        self.max_components = inf.max_components
         self._stats_dev = None
+        self._inflight = {}
         if mask_areas:
             self.set_masks(mask_areas)
 
@@ -77,9 +78,18 @@ class MotionEngine:
         _lib.check(self._lib.fm_ctx_reset(self._ctx, stream))
 
     # -- hot path ---------------------------------------------------------------------------------
-    def process(self, frames, sync=True):
+    @staticmethod
+    def _nvalid(n_valid, S, T):
+        if n_valid is None:
+            return None
+        nv = [int(v) for v in n_valid]
+        assert len(nv) == S and all(0 <= v <= T for v in nv), "n_valid: one count in [0, T] per stream"
+        return (C.c_int32 * S)(*nv)
+
+    def process(self, frames, sync=True, n_valid=None):
         """frames: CUDA uint8 tensor [n_streams, T, H, W, 3] (BGR).  Returns the per-frame stats
-        as a structured numpy array [n_streams, T] (or the device tensor if sync=False)."""
+        as a structured numpy array [n_streams, T] (or the device tensor if sync=False).
+        n_valid: optional per-stream count of real frames in this call (ragged batch)."""
         import torch
 
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5, "uint8 CUDA [S,T,H,W,3]"
@@ -91,23 +101,53 @@ class MotionEngine:
             self._stats_dev = torch.empty(S * self.max_frames * STATS_DTYPE.itemsize, dtype=torch.uint8,
                                           device=frames.device)
         st = torch.cuda.current_stream(frames.device).cuda_stream
-        _lib.check(self._lib.fm_process(self._ctx, frames.data_ptr(), frames.stride(0), frames.stride(1), T,
-                                        C.c_void_p(st), self._stats_dev.data_ptr()))
+        _lib.check(self._lib.fm_process_ragged(self._ctx, frames.data_ptr(), frames.stride(0), frames.stride(1), T,
+                                               self._nvalid(n_valid, S, T), C.c_void_p(st), self._stats_dev.data_ptr()))
         if not sync:
             return self._stats_dev[:need]
         host = self._stats_dev[:need].cpu().numpy()
+        self.check()
         return host.view(STATS_DTYPE).reshape(S, T)
+
+    def check(self):
+        """Synchronise and raise if a call since the last check hit a device-side capacity error."""
+        _lib.check(self._lib.fm_ctx_check(self._ctx))
+
+    @staticmethod
+    def _host_view(frames):
+        """-> (object that owns the memory, pointer, shape, stream stride, frame stride); frames must be dense."""
+        if hasattr(frames, "data_ptr"):
+            assert frames[0, 0].is_contiguous()
+            return frames, frames.data_ptr(), tuple(frames.shape), frames.stride(0), frames.stride(1)
+        frames = np.asarray(frames)
+        if frames.dtype != np.uint8 or not frames[0, 0].flags["C_CONTIGUOUS"]:
+            frames = np.ascontiguousarray(frames, np.uint8)
+        return frames, frames.ctypes.data, frames.shape, frames.strides[0], frames.strides[1]
+
+    def submit_host(self, slot, frames, n_valid=None):
+        """Pipelined host entry: enqueue the batch [n_streams, T, H, W, 3] (host array / pinned tensor) on slot 0 or 1
+        and return; wait_host(slot) gives its stats.  The buffer must stay untouched until then."""
+        frames, ptr, shape, s0, s1 = self._host_view(frames)
+        S, T, H, W, ch = shape
+        assert (S, H, W, ch) == (self.n_streams, self.H, self.W, 3), "frame geometry mismatch"
+        _lib.check(self._lib.fm_submit_host(self._ctx, slot, C.c_void_p(ptr), s0, s1, T, self._nvalid(n_valid, S, T)))
+        self._inflight[slot] = (T, frames)          # keeps the buffer alive
+
+    def submit_reset(self, stream):
+        """reset(stream) ordered with the submitted batches: takes effect after the batches already submitted and
+        before the next one (a slot of a batched context changing over to the next file)."""
+        _lib.check(self._lib.fm_submit_reset(self._ctx, stream))
+
+    def wait_host(self, slot):
+        T, _ = self._inflight.pop(slot)
+        out = np.empty((self.n_streams, T), STATS_DTYPE)
+        _lib.check(self._lib.fm_wait(self._ctx, slot, C.c_void_p(out.ctypes.data)))
+        return out
 
     def process_host(self, frames):
         """frames: host uint8 array / pinned tensor [n_streams, T, H, W, 3].  Copies in, runs,
         copies the stats out (the end-to-end call of the drop-in adapter)."""
-        if hasattr(frames, "data_ptr"):
-            ptr, shape = frames.data_ptr(), tuple(frames.shape)
-            s0, s1 = frames.stride(0), frames.stride(1)
-        else:
-            frames = np.ascontiguousarray(frames)
-            ptr, shape = frames.ctypes.data, frames.shape
-            s0, s1 = frames.strides[0], frames.strides[1]
+        frames, ptr, shape, s0, s1 = self._host_view(frames)
         S, T, H, W, ch = shape
         assert (S, H, W, ch) == (self.n_streams, self.H, self.W, 3), "frame geometry mismatch"
         out = np.empty((S, T), STATS_DTYPE)
@@ -120,14 +160,16 @@ class MotionEngine:
         buf = (_lib.fm_component * max_n)()
         n = C.c_int(0)
         _lib.check(self._lib.fm_get_components(self._ctx, stream, t, max_n, buf, C.byref(n)))
-        m = min(n.value, max_n)
+        m = min(n.value, max_n, self.max_components)     # records the device kept; n is the true count
         return n.value, [(buf[i].area_x2, (buf[i].x, buf[i].y, buf[i].w, buf[i].h)) for i in range(m)]
 
     def motion_boxes(self, stream, t):
         """The rectangles `--show` would draw for frame t (find_motion.py:690-692, 787-813): for every contour
         that find_movement counts, make_area_from_rect(boundingRect) scaled back to source pixels with
         scale_area(area, 1 / scale) (int() truncation).  Sorted."""
-        _, comps = self.components(stream, t)
+        n, comps = self.components(stream, t)
+        if n > len(comps):
+            raise _lib.FmError(-4, f"frame has {n} contours, only {len(comps)} kept: raise max_components")
         inv = 1 / self.info["scale"]
         out = []
         for area2, (x, y, w, h) in comps:
@@ -176,6 +218,30 @@ def label_components(plane: np.ndarray, device=0, max_n=65536):
     n = C.c_int(0)
     _lib.check(lib.fm_debug_components(device, C.c_void_p(plane.ctypes.data), w, h, max_n, buf, C.byref(n)))
     return [(buf[i].area_x2, (buf[i].x, buf[i].y, buf[i].w, buf[i].h)) for i in range(min(n.value, max_n))]
+
+
+class PinnedBatch:
+    """uint8 numpy array in pinned host memory next to `device` (fm_host_alloc), for frame batches."""
+
+    def __init__(self, shape, device=0):
+        self._lib = _lib.load()
+        n = int(np.prod(shape))
+        p, node = C.c_void_p(), C.c_int(-1)
+        _lib.check(self._lib.fm_host_alloc(device, n, C.byref(p), C.byref(node)))
+        self._ptr, self.numa_node = p, node.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            self._lib.fm_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def launch_count() -> int:

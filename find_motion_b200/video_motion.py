@@ -4,9 +4,11 @@ replaced by the B200 path (libfmgpu.so through MotionEngine).
 
 Same constructor keywords, same derived parameters, same `(wrote_frames, err_msg, seen_objects)`
 result, same output files: decode (`cap.read`) and encode (`outfile.write(frame.raw)`) stay on
-the host exactly as in the reference; frames are batched `chunk` at a time, the GPU returns the
-per-frame decisions, and the adapter replays decide_output's cache/flush/write actions in frame
-order on the raw frames it kept.  Display (`show`), Haar cascades and YOLO are outside the hot
+the host exactly as in the reference; frames are batched `chunk` at a time into pinned host memory,
+the GPU returns the per-frame decisions, and the adapter replays decide_output's cache/flush/write
+actions in frame order on the raw frames.  Batches are pipelined: while batch i is on the GPU the
+host decodes batch i+1 and replays batch i-1.  Many files / cameras are batched into one context per
+GPU by find_motion_b200.jobs (run_pool / run_map / run_stream).  Display (`show`), Haar cascades and YOLO are outside the hot
 path and are ignored with a warning.
 """
 from __future__ import annotations
@@ -18,7 +20,7 @@ from collections import deque
 
 import numpy as np
 
-from .engine import MotionEngine
+from .engine import MotionEngine, PinnedBatch
 
 log = logging.getLogger("find_motion")
 
@@ -37,7 +39,7 @@ class VideoMotion(object):
                  multiprocess: bool = False,
                  cascades: typing.List[str] = None,
                  yolo_tiny: bool = False, *,
-                 device: int = 0, chunk: int = 16) -> None:
+                 device: int = 0, chunk: int = 16, engine: typing.Any = None) -> None:
         self.filename = filename
         if self.filename is None:
             raise Exception('Filename required')                      # find_motion.py:311
@@ -47,7 +49,7 @@ class VideoMotion(object):
         self.outfile = None
         self.outfiles = 0
         self.outfile_name = ''
-        self.outdir = os.path.normpath(outdir) if outdir != '' else ''
+        self.outdir = os.path.normpath(outdir)                        # :326 ('' becomes '.', as in the reference)
         self.fps = fps
         self.box_size = box_size
         self.min_box_scale = min_box_scale
@@ -82,14 +84,18 @@ class VideoMotion(object):
         self.seen_objects: typing.Set[str] = set()
         self.frames_read = 0
         self.frames_written = 0
-        self.engine: typing.Optional[MotionEngine] = None
+        # engine=False: the stream is one slot of a batched context driven by find_motion_b200.jobs
+        self._own_engine = engine is None
+        self.engine: typing.Optional[MotionEngine] = engine if engine not in (None, False) else None
         self.loaded = self._load_video()
 
     # -- I/O (host side, as in the reference) ---------------------------------------------------
     def _open_capture(self):
+        self._cv_capture = False
         if hasattr(self.filename, 'read') and hasattr(self.filename, 'get'):
             return self.filename                                     # capture-like object (tests, cameras)
         import cv2
+        self._cv_capture = True
         return cv2.VideoCapture(self.filename)                        # :413
 
     def _get_video_info(self) -> None:
@@ -109,14 +115,18 @@ class VideoMotion(object):
         except VideoError as e:
             self.log.error(str(e))
             return False
-        self.engine = MotionEngine(self.frame_width, self.frame_height, n_streams=1, max_frames=self.chunk,
-                                   device=self.device, mask_areas=self.mask_areas, **self._tuning)
-        inf = self.engine.info
+        if self._own_engine:
+            self.engine = MotionEngine(self.frame_width, self.frame_height, n_streams=1, max_frames=self.chunk,
+                                       device=self.device, mask_areas=self.mask_areas, **self._tuning)
+        if self.engine is not None:
+            self._adopt_info(self.engine.info)
+        return True
+
+    def _adopt_info(self, inf) -> None:
         self.scale = inf["scale"]
         self.max_area = inf["max_area"]
         self.min_area = inf["min_area"]
         self.gaussian = (inf["gaussian"], inf["gaussian"])
-        return True
 
     def _make_outfile(self) -> None:                                   # :443-475
         import cv2
@@ -151,13 +161,15 @@ class VideoMotion(object):
             self.cap.release()
         if self.outfile is not None:
             self.outfile.release()
-        if self.engine is not None:
+        if self.engine is not None and self._own_engine:
             self.engine.close()
-            self.engine = None
+        self.engine = None
 
     # -- main loop ----------------------------------------------------------------------------------
     def _replay(self, raws, stats) -> None:
-        """decide_output's actions on the raw frames, in frame order (find_motion.py:549-589)."""
+        """decide_output's actions on the raw frames, in frame order (find_motion.py:549-589).  `raws` may be views
+        of a staging buffer that is about to be reused: frames that go into the cache are copied (the reference
+        copies every frame, find_motion.py:236), frames that are written are written from where they lie."""
         for raw, st in zip(raws, stats):
             self.movement = bool(st["movement"])
             self.movement_counter = int(st["movement_counter"])
@@ -169,31 +181,60 @@ class VideoMotion(object):
                         self.output_raw_frame(cached)
                     self.frame_cache.clear()
                 self.output_raw_frame(raw)
-            else:
-                self.frame_cache.append(raw)
+            elif self.cache_frames > 0:
+                self.frame_cache.append(raw.copy() if self._copy_cached else raw)
             assert len(self.frame_cache) == int(st["cache_len"]), "frame cache out of step with the device"
+
+    _copy_cached = True
+
+    def read_chunk(self, dst: np.ndarray) -> int:
+        """Decode up to len(dst) frames into dst ([n, H, W, 3] uint8, e.g. a slice of a pinned batch); returns
+        the number read (fewer than len(dst) = end of stream).  find_motion.py:497-506."""
+        n = 0
+        shape = (self.frame_height, self.frame_width, 3)
+        while n < len(dst):
+            if self._cv_capture:
+                ret, frame = self.cap.read(dst[n])                   # decoded straight into the batch when cv2 can
+            else:
+                ret, frame = self.cap.read()
+            if not ret:
+                break
+            if frame.shape != shape or frame.dtype != np.uint8:
+                raise VideoError('frame geometry changed mid-stream: {}'.format(frame.shape))
+            if frame.ctypes.data != dst[n].ctypes.data:
+                dst[n] = frame
+            n += 1
+        self.frames_read += n
+        return n
 
     def find_motion(self) -> tuple:
         """Main loop (find_motion.py:852-904): returns (wrote_frames, err_msg, seen_objects)."""
-        batch = np.empty((1, self.chunk, self.frame_height, self.frame_width, 3), np.uint8)
-        while self.is_open():
-            raws = []
-            while len(raws) < self.chunk:
-                ret, frame = self.cap.read()
-                if not ret:
+        if self.engine is None:
+            raise VideoError('this stream is a slot of a batched context: drive it through find_motion_b200.jobs')
+        shape = (1, self.chunk, self.frame_height, self.frame_width, 3)
+        bufs = [PinnedBatch(shape, self.device) for _ in range(3)]
+        try:
+            pending = None                                            # (slot, host buffer, frames) of the batch in flight
+            i = 0
+            while True:
+                host = bufs[i % 3].array
+                n = self.read_chunk(host[0]) if self.is_open() else 0
+                if n:
+                    self.engine.submit_host(i & 1, host[:, :n])
+                if pending is not None:                               # replay batch i-1 while batch i is on the GPU
+                    pslot, phost, pn = pending
+                    self._replay(phost[0, :pn], self.engine.wait_host(pslot)[0])
+                pending = (i & 1, host, n) if n else None
+                if n < self.chunk:
                     break
-                if frame.shape != (self.frame_height, self.frame_width, 3) or frame.dtype != np.uint8:
-                    raise VideoError('frame geometry changed mid-stream: {}'.format(frame.shape))
-                batch[0, len(raws)] = frame
-                raws.append(frame)
-            if not raws:
-                break
-            self.frames_read += len(raws)
-            stats = self.engine.process_host(batch[:, :len(raws)])
-            self._replay(raws, stats[0])
-            if len(raws) < self.chunk:
-                break
-        self.cleanup()
+                i += 1
+            if pending is not None:
+                pslot, phost, pn = pending
+                self._replay(phost[0, :pn], self.engine.wait_host(pslot)[0])
+        finally:
+            self.cleanup()
+            for b in bufs:
+                b.free()
         return self.wrote_frames, self.err_msg, tuple(self.seen_objects)
 
 

@@ -55,9 +55,6 @@ typedef struct fm_config {
 
 #define FM_FLAG_KEEP_PLANES 1   /* keep gray/blur planes of the last call for fm_debug_planes */
 #define FM_FLAG_NO_FUSED    2   /* force the generic multi-kernel front end (A/B testing) */
-#define FM_FLAG_OVERLAP     4   /* experimental: split a call in two halves and run the contour stage of the
-                                   first on a side stream under K1 of the second (measured slower on B200:
-                                   the labelling CTAs evict K1 CTAs and the background is streamed twice) */
 
 /* Derived parameters, exactly as the reference computes them. */
 typedef struct fm_info {
@@ -71,7 +68,7 @@ typedef struct fm_info {
     int32_t words_per_row;         /* 32-bit words per row of the bit planes */
     double scale;                  /* box_size / frame_width */
     int32_t front_end;             /* 0 = fused full-res stencil, 1 = generic blur, 2 = resize front end */
-    int32_t reserved;
+    int32_t max_components;        /* component records kept per frame (fm_config.max_components, 0 -> 256) */
 } fm_info;
 
 /* Per-frame result: everything find_movement + decide_output decide (find_motion.py:665-700,
@@ -121,19 +118,50 @@ int fm_ctx_reset(fm_ctx *ctx, int stream);
 int fm_process(fm_ctx *ctx, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
                int n_frames, void *cuda_stream, fm_frame_stats *stats_dev);
 
+/* Ragged batch: stream s carries only n_valid[s] <= n_frames real frames in this call (a HOST array of
+ * n_streams entries; NULL = all n_frames).  Streams are independent jobs of different lengths
+ * (find_motion.py:1071-1075 gives each file / camera its own process): a stream with n_valid[s] == 0 is
+ * left untouched (background, counters), the stats of frames t >= n_valid[s] are zero. */
+int fm_process_ragged(fm_ctx *ctx, const uint8_t *frames, size_t stream_stride, size_t frame_stride,
+                      int n_frames, const int32_t *n_valid, void *cuda_stream, fm_frame_stats *stats_dev);
+
 /* Same with HOST buffers: copies the frames host->device (pinned memory recommended), runs the
  * path, copies the stats back and synchronises.  This is the call a drop-in adapter makes. */
 int fm_process_host(fm_ctx *ctx, const uint8_t *frames_host, size_t stream_stride,
                     size_t frame_stride, int n_frames, fm_frame_stats *stats_host);
 
+/* Pipelined form of fm_process_host on two slots (0, 1): fm_submit_host enqueues the host->device copy
+ * of the batch on the context's copy stream, the hot path and the stats read-back on its compute stream,
+ * and returns at once; fm_wait blocks until that slot's batch is done and hands out its stats
+ * ([n_streams][n_frames]).  Submitting batch i+1 to the other slot before waiting for batch i overlaps its
+ * copy with the kernels of batch i and with the host's replay of decide_output on batch i-1.  Batches run
+ * in submission order.  frames_host must stay untouched until fm_wait(slot) returns.  n_valid as in
+ * fm_process_ragged (only the real frames are copied). */
+int fm_submit_host(fm_ctx *ctx, int slot, const uint8_t *frames_host, size_t stream_stride,
+                   size_t frame_stride, int n_frames, const int32_t *n_valid);
+int fm_wait(fm_ctx *ctx, int slot, fm_frame_stats *stats_host);
+/* fm_ctx_reset(stream) ordered with the submitted batches instead of synchronising: it takes effect after the
+ * batches already submitted and before the next one (a slot changes over to the next file, find_motion.py:1075). */
+int fm_submit_reset(fm_ctx *ctx, int stream);
+
+/* Pinned (page-locked) host memory for frame batches, first touched from a thread bound to the CPUs that
+ * are local to `device` (when the platform exposes the GPU's NUMA node; *numa_node = -1 otherwise). */
+int fm_host_alloc(int device, size_t bytes, void **ptr, int *numa_node);
+int fm_host_free(void *ptr);
+
+/* Synchronises and reports (then clears) a sticky device-side error of the calls since the last check:
+ * FM_ERANGE if a frame exceeded the run capacity of the contour stage.  fm_process is asynchronous and
+ * cannot report it; fm_process_host / fm_wait do. */
+int fm_ctx_check(fm_ctx *ctx);
+
 /* Components (contours) of frame t of the LAST fm_process call, sorted by (area_x2, x, y, w, h).
- * Writes min(n, max_n) records and the true count to *n.  Synchronises. */
+ * Writes min(*n, max_n, fm_info.max_components) records and the true count to *n.  Synchronises. */
 int fm_get_components(fm_ctx *ctx, int stream, int t, int max_n, fm_component *out, int *n);
 
 /* Parity-test taps for frame t of the last call (host buffers, any may be NULL):
  * gray, blur (masked) and dilated thresh are proc_height*proc_width uint8; bg is float64 and is
  * the background AFTER the whole call (so compare it at t = n_frames-1).  gray/blur need
- * FM_FLAG_KEEP_PLANES (the fused front end never materialises them otherwise). */
+ * FM_FLAG_KEEP_PLANES (the fused front ends never materialise them otherwise). */
 int fm_debug_planes(fm_ctx *ctx, int stream, int t, uint8_t *gray, uint8_t *blur, uint8_t *thresh,
                     double *bg);
 

@@ -63,7 +63,7 @@ def test_adapter_writes_reference_frames(name, chunk):
 
             class W:
                 def write(_, frame):
-                    written.append(frame)
+                    written.append(frame.copy())      # the frame lies in a pinned batch that is reused
 
                 def release(_):
                     pass

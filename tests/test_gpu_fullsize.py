@@ -83,10 +83,11 @@ def test_cfg3_64_streams_replicated(mode):
     kw = dict(fps=30, threshold=12, avg=0.1, min_time=0.1, cache_time=0.1, mask_areas=synth.CFG2_MASKS)
     kw.update(dict(box_size=1920, blur_scale=384) if mode == "full_k5" else dict(box_size=100, blur_scale=20))
     clips = [synth.make_clip(W, H, n, seed=3000 + i, fps=30, script=[("walker", 1, n), ("blip", 2, 5)]) for i in range(2)]
-    want = []
+    want, orcs = [], []
     for c in clips:
         orc = R.StreamOracle(W, H, **kw)
         want.append([orc.process(f) for f in c])
+        orcs.append(orc)
     dev = torch.stack([torch.from_numpy(clips[s % 2]) for s in range(S)]).cuda()
     with MotionEngine(W, H, n_streams=S, max_frames=4, **kw) as eng:
         got = np.concatenate([eng.process(dev[:, 0:4]), eng.process(dev[:, 4:6])], axis=1)
@@ -98,10 +99,12 @@ def test_cfg3_64_streams_replicated(mode):
                 assert (bool(st["movement"]), int(st["movement_counter"]), int(st["movement_decay"]),
                         bool(st["wrote"]), int(st["n_flush"])) == \
                     (rec["movement"], rec["counter"], rec["decay"], rec["wrote"], rec["n_flush"]), (s, t)
-        # the float64 background of replicas is bit-identical, and equals the oracle's
+        # the float64 background of replicas is bit-identical, and equals the oracle's after the 6 frames
         bg0 = eng.planes(0, 1, gray=False, blur=False, thresh=False)["bg"]
         bg62 = eng.planes(62, 1, gray=False, blur=False, thresh=False)["bg"]
+        bg1 = eng.planes(1, 1, gray=False, blur=False, thresh=False)["bg"]
         assert (bg0 == bg62).all()
+        assert (bg0 == orcs[0].bg).all() and (bg1 == orcs[1].bg).all()
         # reset + replay with a different chunking is idempotent
         eng.reset()
         again = np.concatenate([eng.process(dev[:, 0:1]), eng.process(dev[:, 1:4]), eng.process(dev[:, 4:6])], axis=1)

@@ -73,13 +73,11 @@ def test_fused_equals_generic_front_end():
     clips = np.stack([synth.make_clip(W, H, n, seed=90 + s, fps=10) for s in range(3)])
     dev = torch.from_numpy(clips).cuda()
     with MotionEngine(W, H, n_streams=3, max_frames=T, **kw) as a, \
-            MotionEngine(W, H, n_streams=3, max_frames=T, no_fused=True, **kw) as b, \
-            MotionEngine(W, H, n_streams=3, max_frames=T, overlap=True, **kw) as c:
+            MotionEngine(W, H, n_streams=3, max_frames=T, no_fused=True, **kw) as b:
         assert a.info["front_end"] == 0 and b.info["front_end"] == 1
         for t0 in range(0, n, T):
             sa, sb = a.process(dev[:, t0:t0 + T]), b.process(dev[:, t0:t0 + T])
             assert (sa == sb).all()
-            assert (sa == c.process(dev[:, t0:t0 + T])).all()      # two-half pipelining changes nothing
             for s in range(3):
                 pa, pb = a.planes(s, T - 1, gray=False, blur=False), b.planes(s, T - 1, gray=False, blur=False)
                 assert (pa["thresh"] == pb["thresh"]).all() and (pa["bg"] == pb["bg"]).all()

@@ -14,8 +14,9 @@ def test_shard_streams_partitions():
     from find_motion_b200.sharding import shard_streams
     for n in (1, 7, 8, 64, 65):
         for world in (1, 2, 4, 8):
-            got = [s for r in range(world) for s in shard_streams(n, world, r)]
+            got = sorted(s for r in range(world) for s in shard_streams(n, world, r))
             assert got == list(range(n))
+            assert all(s % world == r for r in range(world) for s in shard_streams(n, world, r))
             sizes = [len(shard_streams(n, world, r)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
 
