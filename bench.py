@@ -41,7 +41,10 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=8, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="T: frames per stream per step")
     ap.add_argument("--ring", type=int, default=32, help="frames per stream resident in HBM")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=32)
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="the timed region repeats the K-step block until it lasts at least this long (sustained clocks); "
+                         "0 = exactly K steps")
     ap.add_argument("--size", default="1920x1080", help="frame size WxH (the headline metric is 1080p)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic clips (0 = one per stream); "
                     "streams reuse them round-robin (large-batch sweeps)")
@@ -119,20 +122,6 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(args, info, dom):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same workload (profiles/r1r_fused_ncu_full.json); null if the
-    workload differs from the captured one."""
-    try:
-        if dom != "front_end" or (W, H, args.streams, args.frames, args.mode) != (1920, 1080, 8, 16, "full") or \
-                info["gaussian"] > 5:
-            return None
-        with open(os.path.join(ROOT, "profiles", "r1r_fused_ncu_full.json")) as f:
-            return int(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:
-        return None
-
-
 def cpu_baseline(kw, cores, target_s=2.5):
     """Reference CPU path on a bounded sample: one stream per process over all host cores."""
     from oracle import cv2_chain
@@ -140,10 +129,26 @@ def cpu_baseline(kw, cores, target_s=2.5):
     per_frame = probe["seconds"] / 4
     frames = max(4, min(400, int(target_s / per_frame)))
     r = cv2_chain.time_cpu_path(W, H, kw, cores, frames, cores, clip_len=8)
-    return {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["processes"], "kind": "port",
-            "sample": f"{cores} synthetic 1080p streams x {frames} frames, one process per stream "
-                      f"({r['engine']}, cv2 threads/process = {r['cv_threads']}), decode/encode excluded",
-            "seconds": round(r["seconds"], 3)}
+    out = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["processes"], "kind": "port",
+           "sample": f"{cores} synthetic {W}x{H} streams x {frames} frames, one process per stream "
+                     f"({r['engine']}, cv2 threads/process = {r['cv_threads']}), decode/encode excluded",
+           "seconds": round(r["seconds"], 3)}
+    # the two other variants SURVEY.md 8(d) asks for (bounded to a few seconds each)
+    variants = {}
+    try:
+        v = cv2_chain.time_cpu_path(W, H, kw, cores, max(4, frames // 2), cores, clip_len=8, cv_threads=0)
+        variants["cv2_threads_default_oversubscribed"] = {
+            "value": round(v["fps"], 2), "unit": "frames/s",
+            "sample": f"{cores} processes, cv2 threads = cores in each (the reference's implicit default), from memory"}
+        nf = max(4, min(64, frames // 4))
+        v = cv2_chain.time_cpu_path(W, H, kw, cores, nf, cores, clip_len=8, source="ffv1")
+        variants["ffv1_decode_included"] = {
+            "value": round(v["fps"], 2), "unit": "frames/s",
+            "sample": f"{cores} processes x {nf} frames pulled through cv2.VideoCapture from a lossless FFV1 file each"}
+    except Exception as e:
+        variants["error"] = str(e)[:200]
+    out["variants"] = variants
+    return out
 
 
 def run_reference(args):
@@ -208,14 +213,32 @@ def time_engine(eng, ring_dev, args, torch, dist, world):
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
+    # how often the K-step block must repeat for the timed region to last --min-seconds (same count on every rank)
+    reps = 1
+    if getattr(args, "min_seconds", 0) > 0:
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        c1.record()
+        torch.cuda.synchronize()
+        est = torch.tensor([c0.elapsed_time(c1) / 1e3], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(est, op=dist.ReduceOp.MIN)
+        reps = max(1, int(-(-args.min_seconds // max(float(est.item()), 1e-6))))
+    if hasattr(eng, "timing"):
+        eng.timing(reset=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from find_motion_b200.engine import launch_count
+    l0 = launch_count()
     e0.record()
-    for i in range(args.steps):
+    for i in range(args.steps * reps):
         step(args.warmup + i)
     e1.record()
+    launches = launch_count() - l0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -224,7 +247,8 @@ def time_engine(eng, ring_dev, args, torch, dist, world):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return ms
+    eng.check()
+    return ms, args.steps * reps, launches
 
 
 def main():
@@ -247,6 +271,58 @@ def main():
         print(json.dumps(line), flush=True)
 
 
+def measure(eng, ring_dev, args, torch, dist, world, S, T, launch_count, local):
+    """Timed region of one regime: throughput, per-kernel-group times (CUDA events on the launching stream, recorded
+    inside the timed region), launch count and the clocks seen under load."""
+    eng.timing(enable=True, reset=True)
+    for i in range(2):                       # untimed priming pass
+        eng.process(ring_dev[:, :T], sync=False)
+    torch.cuda.synchronize()
+    eng.reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, timed_steps, launches = time_engine(eng, ring_dev, args, torch, dist, world)
+    clocks = sampler.stop()
+    groups = eng.timing()                    # reset at the start of the timed region: timed steps only
+    fps = S * T * timed_steps * world / (ms / 1e3)
+    per_call = {k: v[0] / max(1, v[1]) for k, v in groups.items()}
+    eng.timing(enable=False)
+    return {"fps": fps, "ms": ms, "timed_steps": timed_steps, "step_ms": ms / timed_steps, "per_call": per_call,
+            "launches": int(launches), "clocks": clocks}
+
+
+def roofline_of(m, info, S, T, traffic=None):
+    per_call = m["per_call"]
+    dom = max(per_call, key=per_call.get)
+    peak, peak_src = hbm_peak()
+    balg = alg_bytes_per_frame(info["proc_width"], info["proc_height"], T)
+    bytes_launch = balg * S * T
+    achieved = bytes_launch / (per_call[dom] / 1e3) / 1e9
+    r = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+         "frac": round(achieved / peak, 4), "traffic": None, "kernel": dom,
+         "kernel_ms_per_launch": round(per_call[dom], 4), "peak_source": peak_src,
+         "alg_bytes_per_frame": round(balg), "alg_formula": "3*W*H + (16/T)*w*h + m*w*h, m=1/8 (bit-packed mask)",
+         "groups_ms_per_step": {k: round(v, 4) for k, v in per_call.items()},
+         "whole_step_frac": round(bytes_launch / (m["step_ms"] / 1e3) / 1e9 / peak, 4)}
+    if traffic:
+        r["traffic"], r["traffic_source"] = traffic
+    return r
+
+
+def ncu_traffic_for(args, info, name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: NOT measured by this run (a
+    number taken under a profiler is never a bench value) -- read from the committed `ncu --set full` capture of this
+    same command line, and labelled with its file; null when the workload differs from the captured one."""
+    try:
+        if (W, H, args.streams, args.frames) != (1920, 1080, 8, 16):
+            return None
+        path = os.path.join("profiles", f"r2_{name}_ncu_full.json")
+        with open(os.path.join(ROOT, path)) as f:
+            return int(json.load(f)["traffic_bytes_per_launch"]), path + " (ncu --set full of the same command)"
+    except Exception:
+        return None
+
+
 def run_b200(args):
 
     import numpy as np
@@ -254,7 +330,8 @@ def run_b200(args):
     import torch.distributed as dist
 
     from find_motion_b200 import synth
-    from find_motion_b200.engine import MotionEngine, launch_count
+    from find_motion_b200.engine import MotionEngine, PinnedBatch, launch_count
+    from find_motion_b200.sharding import gather_stats, shard_streams
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -267,6 +344,7 @@ def run_b200(args):
 
     kw = tuning(args.mode, args.blur_scale)
     S, T, R = args.streams, args.frames, args.ring
+    my_streams = shard_streams(S * world, world, rank)          # stream s of the job lives on rank s mod G
 
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
     cpu = None
@@ -276,128 +354,140 @@ def run_b200(args):
         except Exception as e:   # never let the baseline kill the measurement
             cpu = {"error": str(e)[:200]}
 
-    # synthetic streams: seed = 1000*cfg + global stream id, resident in HBM
+    # synthetic streams: seed = 1000*cfg + global stream id, resident in HBM; the host copy lives in
+    # pinned memory allocated next to this rank's GPU (fm_host_alloc)
     nd = min(S, args.distinct) if args.distinct else S
+    ring_pin = None
     if nd == S:
-        ring_host = torch.empty((S, R, H, W, 3), dtype=torch.uint8).pin_memory()
-        for s in range(S):
-            clip = synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + s), script=bench_script(R))
-            ring_host[s] = torch.from_numpy(clip)
-        ring_dev = ring_host.cuda(non_blocking=True)
+        ring_pin = PinnedBatch((S, R, H, W, 3), local)
+        for i, s in enumerate(my_streams):
+            ring_pin.array[i] = synth.make_clip(W, H, R, synth.stream_seed(2, s), script=bench_script(R))
+        ring_host = torch.from_numpy(ring_pin.array)
+        ring_dev = ring_host.cuda()
     else:
         ring_host = None
         ring_dev = torch.empty((S, R, H, W, 3), dtype=torch.uint8, device="cuda")
         for d in range(nd):
-            clip = torch.from_numpy(synth.make_clip(W, H, R, synth.stream_seed(2, rank * S + d), script=bench_script(R))).cuda()
+            clip = torch.from_numpy(synth.make_clip(W, H, R, synth.stream_seed(2, my_streams[d]), script=bench_script(R))).cuda()
             for s in range(d, S, nd):
                 ring_dev[s] = clip
     torch.cuda.synchronize()
 
     eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **kw)
     info = dict(eng.info, w=eng.w, h=eng.h)
-    eng.timing(enable=True, reset=True)
+    m = measure(eng, ring_dev, args, torch, dist, world, S, T, launch_count, local)
+    name = "fused" if info["front_end"] == 0 else ("wide" if args.mode == "full" else "default")
+    roofline = roofline_of(m, info, S, T, ncu_traffic_for(args, info, name))
 
-    sampler = ClockSampler(local)
-    # untimed priming pass so that the timing ring only sees the timed steps
-    for i in range(2):
-        eng.process(ring_dev[:, :T], sync=False)
-    torch.cuda.synchronize()
+    # NCCL is used only here: the per-frame stats of one more (untimed) step are gathered so that rank 0 can report
+    # motion flags for the whole box
+    last = eng.process(ring_dev[:, :T], sync=True)
+    allstats = gather_stats(last, S * world, dist if world > 1 else None)
+    gathered = {"streams": int(allstats.shape[0]), "frames": int(allstats.size),
+                "motion_frames": int((allstats["movement"] != 0).sum()), "via": "nccl all_gather" if world > 1 else "local"}
+
+    # end to end through the host-buffer entry points: pinned host frames -> H2D -> kernels -> stats D2H every step,
+    # pipelined on two slots (fm_submit_host / fm_wait) exactly as the job driver does it
     eng.reset()
-    eng.timing(reset=True)
-    l0 = launch_count()
-    sampler.start()
-    # NOTE: warm-up steps are launched inside time_engine; their group timings are subtracted below
-    ms = time_engine(eng, ring_dev, args, torch, dist, world)
-    clocks = sampler.stop()
-    launches_total = launch_count() - l0
-    groups = eng.timing()
-    calls = max(1, groups["front_end"][1])
-    launches = int(round(launches_total * args.steps / calls))          # timed steps only
-    frames_job = S * T * args.steps * world
-    fps = frames_job / (ms / 1e3)
-
-    # roofline of the dominant kernel group (CUDA events recorded on the launching stream)
-    per_call = {k: v[0] / max(1, v[1]) for k, v in groups.items()}
-    dom = max(per_call, key=per_call.get)
-    peak, peak_src = hbm_peak()
-    balg = alg_bytes_per_frame(info["proc_width"], info["proc_height"], T)
-    bytes_launch = balg * S * T
-    achieved = bytes_launch / (per_call[dom] / 1e3) / 1e9
-    step_ms = ms / args.steps
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args, info, dom), "kernel": dom,
-                "kernel_ms_per_launch": round(per_call[dom], 4), "peak_source": peak_src,
-                "alg_bytes_per_frame": round(balg), "alg_formula": "3*W*H + (16/T)*w*h + m*w*h, m=1/8 (bit-packed mask)",
-                "groups_ms_per_step": {k: round(v, 4) for k, v in per_call.items()},
-                "whole_step_frac": round(bytes_launch / (step_ms / 1e3) / 1e9 / peak, 4)}
-
-    # end to end through the host-buffer entry point
-    eng.timing(enable=False)
-    eng.reset()
-    if args.no_e2e or ring_host is None:
-        e2e = None
-        return finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, {})
-    host_batch = [ring_host[:, a:a + T] for a in range(0, R, T)]
-    for i in range(2):
-        eng.process_host(host_batch[i % len(host_batch)])
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        eng.process_host(host_batch[i % len(host_batch)])
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = S * T * args.e2e_steps * world / e2e_s
-    e2e = {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": S * T * W * H * 3,
-           "d2h_bytes_per_step": S * T * 32, "steps": args.e2e_steps,
-           "api": "fm_process_host (MotionEngine.process_host), pinned host frames"}
+    e2e = None
+    if not args.no_e2e and ring_host is not None:
+        host_batch = [ring_pin.array[:, a:a + T] for a in range(0, R, T)]
+        nb = len(host_batch)
+        for i in range(2):
+            eng.process_host(host_batch[i % nb])
+        torch.cuda.synchronize()
+        # ceiling: the same bytes through cudaMemcpyAsync alone, all ranks at once
+        stage = torch.empty((S, T, H, W, 3), dtype=torch.uint8, device="cuda")
+        src = [[torch.from_numpy(b[s]) for s in range(S)] for b in host_batch]      # [T, H, W, 3] each, contiguous, pinned
+        for s in range(S):
+            stage[s].copy_(src[0][s], non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(8):
+            for s in range(S):
+                stage[s].copy_(src[i % nb][s], non_blocking=True)
+        torch.cuda.synchronize()
+        copy_s = time.perf_counter() - t0
+        bytes_step = S * T * W * H * 3
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            eng.submit_host(i & 1, host_batch[i % nb])
+            if i:
+                eng.wait_host((i - 1) & 1)
+        eng.wait_host((args.e2e_steps - 1) & 1)
+        e2e_s = time.perf_counter() - t0
+        mine = torch.tensor([e2e_s, copy_s], device="cuda", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        e2e_all = [float(t[0]) for t in allr]
+        copy_all = [float(t[1]) for t in allr]
+        e2e_s = max(e2e_all)
+        e2e = {"value": round(S * T * args.e2e_steps * world / e2e_s, 1), "unit": "frames/s",
+               "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": S * T * 32, "steps": args.e2e_steps,
+               "seconds": round(e2e_s, 3),
+               "h2d_gbs_per_rank": [round(bytes_step * args.e2e_steps / t / 1e9, 1) for t in e2e_all],
+               "h2d_copy_only_gbs_per_rank": [round(bytes_step * 8 / t / 1e9, 1) for t in copy_all],
+               "pinned_numa_node": ring_pin.numa_node,
+               "api": "fm_submit_host / fm_wait (MotionEngine.submit_host / wait_host), two slots, pinned host frames "
+                      "allocated with fm_host_alloc; h2d_copy_only = the same bytes through cudaMemcpyAsync alone on "
+                      "all ranks at once (the platform's ceiling for this path)"}
+        del stage
 
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = secondary_regimes(args, ring_dev, torch, dist)
-    return finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, extras)
-
-
-def finish(args, eng, rank, world, dist, fps, step_ms, kw, info, roofline, cpu, e2e, launches, clocks, extras):
+        extras = secondary_regimes(args, ring_dev, torch, dist, launch_count, local)
     eng.close()
     line = None
     if rank == 0:
+        clocks = dict(m["clocks"])
         line = {
-            "metric": METRIC if (W, H) == (1920, 1080) else f"{W}x{H} frames/sec (whole box)", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if (W, H) == (1920, 1080) else f"{W}x{H} frames/sec (whole box)", "value": round(m["fps"], 1),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(m["step_ms"], 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "config": workload_config(args, kw, info),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "timed_steps": m["timed_steps"], "timed_region_s": round(m["ms"] / 1e3, 3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["launches"], "clocks": clocks,
+            "gathered_stats": gathered,
         }
         if extras:
             line["other_regimes"] = extras
     if world > 1:
         dist.destroy_process_group()
+    if ring_pin is not None:
+        del ring_host
+        ring_pin.free()
     return line
 
 
-def secondary_regimes(args, ring_dev, torch, dist):
-    """Same streams in the other two regimes SURVEY.md 8(d) asks for (reported, not the headline)."""
+def secondary_regimes(args, ring_dev, torch, dist, launch_count, local):
+    """Same streams in the other two regimes SURVEY.md 8(d) asks for, each with its own roofline (the reference's own
+    blur scale, k=97 at 1080p, runs on the tensor cores; the reference's CLI default, box 100, is bound by reading
+    3*W*H)."""
     from find_motion_b200.engine import MotionEngine
     out = {}
     S, T = args.streams, args.frames
-    for name, mode, bs in (("full_k97_alu_bound", "full", 20), ("default_box100", "default", 20)):
+    for name, mode, bs, tag in (("full_k97_reference_blur_scale", "full", 20, "wide"), ("default_box100", "default", 20, "default")):
         if mode == args.mode and (args.blur_scale or (384 if mode == "full" else 20)) == bs:
             continue
         kw = tuning(mode, bs)
         try:
             with MotionEngine(W, H, n_streams=S, max_frames=T, **kw) as eng:
                 a = argparse.Namespace(**vars(args))
-                a.steps, a.warmup = max(3, min(40, args.steps // 4)), 3
-                ms = time_engine(eng, ring_dev, a, torch, dist, 1)
-                fps = S * T * a.steps / (ms / 1e3)
-                balg = alg_bytes_per_frame(eng.w, eng.h, T)
-                peak, _ = hbm_peak()
-                out[name] = {"value": round(fps, 1), "unit": "frames/s", "proc": f"{eng.w}x{eng.h}",
-                             "gaussian": eng.info["gaussian"], "steps": a.steps,
-                             "hbm_frac_whole_step": round(fps * balg / 1e9 / peak, 4)}
+                a.steps, a.warmup, a.min_seconds = max(3, min(40, args.steps // 4)), 3, min(args.min_seconds, 1.0)
+                info = dict(eng.info, w=eng.w, h=eng.h)
+                m = measure(eng, ring_dev, a, torch, dist, 1, S, T, launch_count, local)
+                out[name] = {"value": round(m["fps"], 1), "unit": "frames/s", "proc": f"{eng.w}x{eng.h}",
+                             "gaussian": eng.info["gaussian"], "timed_steps": m["timed_steps"],
+                             "ms_per_step": round(m["step_ms"], 4),
+                             "roofline": roofline_of(m, info, S, T, ncu_traffic_for(args, info, tag)),
+                             "clocks": m["clocks"]}
         except Exception as e:
             out[name] = {"error": str(e)[:200]}
     return out

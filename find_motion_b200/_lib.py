@@ -45,6 +45,7 @@ class fm_component(C.Structure):
 
 FLAG_KEEP_PLANES = 1
 FLAG_NO_FUSED = 2
+FLAG_NO_UMMA = 8
 
 # every symbol include/fm_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

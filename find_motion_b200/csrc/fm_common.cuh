@@ -13,7 +13,7 @@
 #define FM_MAX_K 1024          // widest supported Gaussian (taps)
 #define FM_TILE_PX 512         // pixels per background tile: 32 lanes x 16 px
 #define FM_TILE_WORDS 16       // 32-bit threshold words per tile
-#define FM_TIMING_RING 1024
+#define FM_TIMING_RING 16384
 #define FM_MAX_DEVICES 64      // per-device caches of kernel attributes (cudaFuncSetAttribute is per device)
 
 struct StreamState {           // per stream, device resident (find_motion.py:362-371)
@@ -50,6 +50,9 @@ struct fm_ctx {
     int resize_mode;           // 0 identity, 1 general tables, 2 integer ratio
     bool fused;                // K1 fused stencil+background kernel drives the front end
     bool wide_fused;           // wide Gaussian: the vertical pass runs the temporal stage too (k_wide_vt)
+    bool umma;                 // blur + temporal stage on tcgen05 tensor cores (k_umma.cu), k <= 97
+    uint8_t *uband;            // band (Toeplitz) operand of the tcgen05 blur
+    uint8_t *gpad;             // [S][Tmax][Hp][Wp] gray plane with the BORDER_REFLECT_101 apron materialised
     int fx, fy;                // integer ratios (mode 2)
     int maxc;
     // tables
@@ -151,6 +154,11 @@ int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_
 int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
+bool fm_umma_supported(const fm_ctx *c);
+int fm_umma_init(fm_ctx *c, const int *taps);
+size_t fm_umma_bg_doubles(const fm_ctx *c);
+int fm_launch_umma_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
+int fm_launch_bg_export_umma(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_ccl_alloc(CclScratch *s, int frames, int h, int cap);
 void fm_ccl_free(CclScratch *s);
 int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n, fm_component *out,

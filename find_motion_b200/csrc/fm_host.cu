@@ -140,7 +140,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(c->coef); cudaFree(c->wtab);
+    cudaFree(c->coef); cudaFree(c->wtab); cudaFree(c->uband); cudaFree(c->gpad);
     cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
@@ -271,13 +271,15 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
         }
     }
     c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);
-    c->wide_fused = !c->fused && fm_wide_fused_supported(c);
+    c->umma = !c->fused && fm_umma_supported(c) && !(cfg->flags & FM_FLAG_NO_UMMA);
+    c->wide_fused = !c->fused && !c->umma && fm_wide_fused_supported(c);
     inf.front_end = c->fused ? 0 : (c->resize_mode == 0 ? 1 : 2);
     {
         std::vector<int> taps = gauss_coeffs(c->k);
         if ((rc = upload(&c->coef, taps))) return fail(rc);
         // the shared-memory needs of the wide blur are checked here, not at the first launch
-        if (!c->fused && (rc = fm_wide_init(c, taps.data()))) return fail(rc);
+        if (c->umma && (rc = fm_umma_init(c, taps.data()))) return fail(rc);
+        if (!c->fused && !c->umma && (rc = fm_wide_init(c, taps.data()))) return fail(rc);
     }
 
     const size_t F = (size_t)c->S * c->Tmax;
@@ -296,10 +298,11 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     const bool need_gray = keep || !c->fused;
     const bool need_blur = keep || !c->fused;
     ALLOC(c->gray, need_gray ? F * c->N : 16);
-    ALLOC(c->hor, c->fused ? 16 : 2 * fm_wide_plane_bytes(c));
+    ALLOC(c->hor, (c->fused || c->umma) ? 16 : 2 * fm_wide_plane_bytes(c));
     ALLOC(c->blur, need_blur ? F * c->N + 64 : 64);
     const size_t bg_doubles = std::max((size_t)c->S * c->ntiles * FM_TILE_PX,
-                                       c->fused ? fm_fused_bg_doubles(c) : (c->wide_fused ? fm_wide_bg_doubles(c) : (size_t)0));
+                                       c->fused ? fm_fused_bg_doubles(c)
+                                                : (c->umma ? fm_umma_bg_doubles(c) : (c->wide_fused ? fm_wide_bg_doubles(c) : (size_t)0)));
     ALLOC(c->bg, bg_doubles * sizeof(double));
     ALLOC(c->maskbits, (size_t)c->S * c->h * c->wpr * 4);
     ALLOC(c->maskflat, (size_t)c->S * flatw * 4);
@@ -457,7 +460,7 @@ extern "C" int fm_process_ragged(fm_ctx *c, const uint8_t *frames, size_t stream
     } else {
         if ((rc = fm_launch_frontend(c, frames, stream_stride, frame_stride, n_frames, st))) return rc;
         if (ev) FM_CUDA(cudaEventRecord(ev[1], st));
-        if (!c->wide_fused && (rc = fm_launch_temporal(c, n_frames, st))) return rc;
+        if (!c->wide_fused && !c->umma && (rc = fm_launch_temporal(c, n_frames, st))) return rc;
         if (ev) FM_CUDA(cudaEventRecord(ev[2], st));
     }
     if ((rc = fm_launch_morph_ccl(c, n_frames, st, stats_dev))) return rc;
@@ -687,8 +690,9 @@ extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint
         DevBuf d;
         FM_CUDA(cudaMalloc(&d.p, (size_t)c->N * sizeof(double)));
         int rc = c->fused ? fm_launch_bg_export_fused(c, stream, (double *)d.p, 0)
-                          : (c->wide_fused ? fm_launch_bg_export_wide(c, stream, (double *)d.p, 0)
-                                           : fm_launch_bg_export(c, stream, (double *)d.p, 0));
+                 : c->umma ? fm_launch_bg_export_umma(c, stream, (double *)d.p, 0)
+                 : c->wide_fused ? fm_launch_bg_export_wide(c, stream, (double *)d.p, 0)
+                                 : fm_launch_bg_export(c, stream, (double *)d.p, 0);
         if (rc) return rc;
         FM_CUDA(cudaMemcpy(bg, d.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
     }

@@ -427,7 +427,8 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
                        cudaStream_t st) {
     const int F = c->S * T;
     // every Gaussian the fused stencil does not take goes to the tensor-core blur (k_wide.cu)
-    if (c->resize_mode == 0) return fm_launch_wide_blur(c, frames, sstride, fstride, T, st);   // gray fused into pass 1
+    if (c->resize_mode == 0)          // gray fused into the first kernel of the blur
+        return c->umma ? fm_launch_umma_blur(c, frames, sstride, fstride, T, st) : fm_launch_wide_blur(c, frames, sstride, fstride, T, st);
     {
         K0Params p;
         p.frames = frames; p.sstride = sstride; p.fstride = fstride;
@@ -486,5 +487,5 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
             FM_LAUNCH_CHECK();
         }
     }
-    return fm_launch_wide_blur(c, nullptr, 0, 0, T, st);
+    return c->umma ? fm_launch_umma_blur(c, nullptr, 0, 0, T, st) : fm_launch_wide_blur(c, nullptr, 0, 0, T, st);
 }

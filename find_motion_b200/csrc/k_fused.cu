@@ -432,7 +432,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled fm_tma_encoder() {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *sym = nullptr;
@@ -451,7 +451,7 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
         fm_set_error("fused front end needs 16-byte aligned frames and strides (TMA)");
         return FM_EINVAL;
     }
-    PFN_encodeTiled enc = get_encode();
+    PFN_encodeTiled enc = fm_tma_encoder();
     if (!enc) { fm_set_error("cuTensorMapEncodeTiled not available"); return FM_ECUDA; }
     // the call's frames as a 4-D u32 tensor: (W*3/4 words, H rows, T frames, S streams)
     CUtensorMap tmap;

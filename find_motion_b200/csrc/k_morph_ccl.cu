@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t dilate_row(const uint32_t *__restrict__ flat
             if (rem < 32) d &= (1u << rem) - 1u;
             out[j] = d;
             anyw |= d;
-            if (d) { jmax = j; jmin = min(jmin, j); }
+            if (d) { jmax = max(jmax, j); jmin = min(jmin, j); }      // a lane walks several words and (in the labelling kernel) several rows
         }
         vprev = vc;
         vc = vnext;

@@ -614,8 +614,29 @@ int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_
 // identity-resize gray plane (parity tap of the fused conversion), defined in k_frontend.cu
 int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 
+// k = 1: GaussianBlur is the identity, only the polygon masks are painted (find_motion.py:494, 619-635)
+__global__ void __launch_bounds__(256) k_blur_identity(const uint8_t *__restrict__ gray, uint8_t *__restrict__ blur,
+                                                       const uint32_t *__restrict__ maskbits, int w, int h, int wpr, int T,
+                                                       const int *__restrict__ nvalid) {
+    const int f = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w || f % T >= __ldg(nvalid + f / T)) return;
+    const uint32_t m = __ldg(maskbits + ((size_t)(f / T) * h + y) * wpr + (x >> 5));
+    const size_t i = ((size_t)f * h + y) * w + x;
+    blur[i] = ((m >> (x & 31)) & 1u) ? (uint8_t)0 : gray[i];
+}
+
 // frames != nullptr: full-resolution mode, convert BGR -> gray while staging (no gray plane); else read c->gray
 int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st) {
+    if (c->k == 1) {
+        if (frames) {
+            int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
+            if (rc) return rc;
+        }
+        dim3 grid((c->w + 255) / 256, c->h, c->S * T);
+        k_blur_identity<<<grid, 256, 0, st>>>(c->gray, c->blur, c->maskbits, c->w, c->h, c->wpr, T, c->nvalid);
+        FM_LAUNCH_CHECK();
+        return FM_OK;
+    }
     const WideGeom g = wide_geom(c);
     const int F = c->S * T;
     uint32_t *plo = reinterpret_cast<uint32_t *>(c->hor);

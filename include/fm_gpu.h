@@ -55,6 +55,7 @@ typedef struct fm_config {
 
 #define FM_FLAG_KEEP_PLANES 1   /* keep gray/blur planes of the last call for fm_debug_planes */
 #define FM_FLAG_NO_FUSED    2   /* force the generic multi-kernel front end (A/B testing) */
+#define FM_FLAG_NO_UMMA     8   /* wide Gaussian on the mma.sync two-pass path instead of the tcgen05 one-pass kernel (A/B) */
 
 /* Derived parameters, exactly as the reference computes them. */
 typedef struct fm_info {

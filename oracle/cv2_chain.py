@@ -114,25 +114,48 @@ def _worker(spec):
         clip = synth.make_clip(W, H, spec["clip_len"], seed, fps=kw.get("fps", 30))
         if spec["use_cv2"]:
             import cv2
-            cv2.setNumThreads(spec["cv_threads"])
+            if spec["cv_threads"] > 0:            # 0 = the reference's implicit default (cv2 threads = cores)
+                cv2.setNumThreads(spec["cv_threads"])
             step = Cv2Stream(W, H, **kw).step
         else:
             from oracle import restated as R
             step = R.StreamOracle(W, H, **kw).process
+        if spec.get("source") == "ffv1" and spec["use_cv2"]:
+            # decode included: the clip is written once as a lossless FFV1 file (untimed) and the timed loop pulls its
+            # frames through cv2.VideoCapture.read(), re-opening the file when it is exhausted (find_motion.py:497-506)
+            import os
+            import tempfile
+            path = os.path.join(tempfile.mkdtemp(prefix="fm_cpu_"), "clip_%d.avi" % seed)
+            wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), kw.get("fps", 30), (W, H))
+            for f in clip:
+                wr.write(f)
+            wr.release()
+            state = {"cap": cv2.VideoCapture(path)}
+
+            def next_frame(i):
+                ok, f = state["cap"].read()
+                if not ok:
+                    state["cap"].release()
+                    state["cap"] = cv2.VideoCapture(path)
+                    ok, f = state["cap"].read()
+                return f
+        else:
+            def next_frame(i):
+                return clip[i % spec["clip_len"]]
         moved, i = 0, 0
         for _ in range(warmup * spec["frames"]):
-            step(clip[i % spec["clip_len"]])
+            step(next_frame(i))
             i += 1
         t0 = time.perf_counter()
         for _ in range(steps * spec["frames"]):
-            moved += int(step(clip[i % spec["clip_len"]])["movement"])
+            moved += int(step(next_frame(i))["movement"])
             i += 1
         out.append({"seconds": time.perf_counter() - t0, "moved": moved})
     return out
 
 
 def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8, seed0=2000, cv_threads=1,
-                  timeout=900, steps=1, warmup=0):
+                  timeout=900, steps=1, warmup=0, source="memory"):
     """Run `n_streams` synthetic streams over `processes` worker processes (streams dealt round-robin);
     every stream does `warmup` untimed + `steps` timed steps of `frames_per_stream` frames.
     Returns dict(fps, seconds, frames, processes, engine)."""
@@ -147,7 +170,7 @@ def time_cpu_path(W, H, kw, n_streams, frames_per_stream, processes, clip_len=8,
     for p in range(processes):
         spec = {"W": W, "H": H, "kw": kw, "seeds": [seed0 + s for s in range(p, n_streams, processes)],
                 "clip_len": clip_len, "frames": frames_per_stream, "cv_threads": cv_threads, "use_cv2": use_cv2,
-                "steps": steps, "warmup": warmup}
+                "steps": steps, "warmup": warmup, "source": source}
         procs.append(subprocess.Popen([sys.executable, "-m", "oracle.cv2_chain", json.dumps(spec)], cwd=root,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     busy = 0.0

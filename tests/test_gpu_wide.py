@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(W, H, n, T, kw, seed, n_streams=1, expect_front_end=None):
+def _run(W, H, n, T, kw, seed, n_streams=1, expect_front_end=None, **engine_kw):
     import torch
     from find_motion_b200 import synth
     from find_motion_b200.engine import MotionEngine
@@ -15,7 +15,7 @@ def _run(W, H, n, T, kw, seed, n_streams=1, expect_front_end=None):
     clips = np.stack([synth.make_clip(W, H, n, seed=seed + s, fps=kw.get("fps", 30)) for s in range(n_streams)])
     orcs = [R.StreamOracle(W, H, **kw) for _ in range(n_streams)]
     dev = torch.from_numpy(clips).cuda()
-    with MotionEngine(W, H, n_streams=n_streams, max_frames=T, keep_planes=True, **kw) as eng:
+    with MotionEngine(W, H, n_streams=n_streams, max_frames=T, keep_planes=True, **engine_kw, **kw) as eng:
         if expect_front_end is not None:
             assert eng.info["front_end"] == expect_front_end
         for t0 in range(0, n, T):
@@ -51,18 +51,54 @@ GEOMETRIES = [
 ]
 
 
+@pytest.mark.parametrize("no_umma", [False, True])
 @pytest.mark.parametrize("W,H,bs", GEOMETRIES)
-def test_wide_blur_geometries(W, H, bs):
+def test_wide_blur_geometries(W, H, bs, no_umma):
+    """no_umma=False: planes with w % 32 == 0 and k <= 97 take the tcgen05 one-pass kernel (k_umma.cu), the others the
+    mma.sync two-pass kernels; no_umma=True forces the two-pass kernels everywhere."""
     kw = dict(fps=6, box_size=W, blur_scale=bs, threshold=5, avg=0.2, min_time=0.3, cache_time=0.6,
               mask_areas=[((2, 1), (W // 3, H // 2)), ((W // 2, 0), (W - 1, H // 3), (W // 2, H - 1))])
-    _run(W, H, 9, 4, kw, seed=500 + W, expect_front_end=1)
+    _run(W, H, 9, 4, kw, seed=500 + W, expect_front_end=1, no_umma=no_umma)
 
 
-def test_wide_blur_two_streams_mixed_masks():
+@pytest.mark.parametrize("no_umma", [False, True])
+def test_wide_blur_two_streams_mixed_masks(no_umma):
     from find_motion_b200 import synth
     kw = dict(fps=10, box_size=640, blur_scale=20, threshold=8, avg=0.1, min_time=0.2, cache_time=0.4,
               mask_areas=synth.README_MASKS)                  # k = 33
-    _run(640, 360, 10, 5, kw, seed=610, n_streams=2, expect_front_end=1)
+    _run(640, 360, 10, 5, kw, seed=610, n_streams=2, expect_front_end=1, no_umma=no_umma)
+
+
+# tcgen05 kernel: tile grid edges (partial 128 x 128 tiles), every kernel radius class, avg outside [0, 1], resize in front
+UMMA_GEOMETRIES = [
+    (128, 128, 2, None),                 # k = 65, exactly one tile
+    (256, 130, 3, None),                 # k = 85, two tile rows, the second with 2 live rows
+    (160, 100, 2, None),                 # k = 81 > plane height / 2: multiple reflections inside the apron
+    (1280, 720, 256, None),              # k = 5 through the wide path (fused stencil switched off below)
+    (640, 360, 7, None),                 # k = 91
+    (96, 40, 1, None),                   # k = 97 = the largest radius the apron holds, plane smaller than a tile
+    (32, 2, 4, None),                    # k = 9, two rows
+]
+
+
+@pytest.mark.parametrize("W,H,bs,_", UMMA_GEOMETRIES)
+def test_umma_blur_geometries(W, H, bs, _):
+    kw = dict(fps=6, box_size=W, blur_scale=bs, threshold=5, avg=0.2, min_time=0.3, cache_time=0.6,
+              mask_areas=[((2, 1), (W // 3, H // 2)), ((W // 2, 0), (W - 1, H // 3), (W // 2, H - 1))])
+    _run(W, H, 6, 4, kw, seed=900 + W, no_fused=True)
+
+
+def test_umma_blur_avg_outside_unit_range_and_k1():
+    kw = dict(fps=6, box_size=128, blur_scale=9, threshold=6, avg=1.7, min_time=0.3, cache_time=0.5)     # k = 15
+    _run(128, 96, 8, 4, kw, seed=930, no_fused=True)
+    kw = dict(fps=6, box_size=128, blur_scale=128, threshold=6, avg=0.3, min_time=0.3, cache_time=0.5)   # k = 1
+    _run(128, 96, 8, 4, kw, seed=931, no_fused=True)
+
+
+def test_umma_blur_after_resize():
+    """2x integer resize (960x540 -> 480x270 would not be % 32; 1280x720 -> 640x360 is), k = 33 on the resized plane."""
+    kw = dict(fps=8, box_size=640, blur_scale=20, threshold=6, avg=0.15, min_time=0.3, cache_time=0.5)
+    _run(1280, 720, 6, 3, kw, seed=940, expect_front_end=2)
 
 
 def test_wide_blur_after_resize():
