@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--size", default="1920x1080", help="frame size WxH (the headline metric is 1080p)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic clips (0 = one per stream); "
                     "streams reuse them round-robin (large-batch sweeps)")
+    ap.add_argument("--front-end", default="auto", choices=["auto", "stencil", "umma", "umma-apron", "mma-sync"],
+                    help="A/B of the front-end kernels: stencil = k_fused (k <= 5), umma = tcgen05 kernel fed by the BGR frames, "
+                         "umma-apron = tcgen05 kernel through the apron plane, mma-sync = the two-pass mma.sync Gaussian")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary regimes (k=97, default mode)")
@@ -195,6 +198,7 @@ def workload_config(args, kw, info):
         "box_size": kw["box_size"], "blur_scale": kw["blur_scale"], "threshold": kw["threshold"], "avg": kw["avg"],
         "min_time": kw["min_time"], "cache_time": kw["cache_time"], "fps": kw["fps"],
         "streams_per_gpu": args.streams, "frames_per_step_per_stream": args.frames, "ring_frames": args.ring,
+        "front_end": args.front_end,
         "l2_policy": f"inputs larger than L2: ring of {args.ring} frames/stream = "
                      f"{args.streams * args.ring * W * H * 3 / 1e6:.0f} MB per GPU, each step reads the next T frames",
         "parallelism": f"streams sharded over {args.gpus} GPU(s), no data-path collective",
@@ -373,7 +377,9 @@ def run_b200(args):
                 ring_dev[s] = clip
     torch.cuda.synchronize()
 
-    eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **kw)
+    fe = {"auto": {}, "stencil": {}, "umma": dict(no_fused=True, umma=True), "umma-apron": dict(no_fused=True, umma=True, umma_apron=True),
+          "mma-sync": dict(no_fused=True, no_umma=True)}[args.front_end]
+    eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **fe, **kw)
     info = dict(eng.info, w=eng.w, h=eng.h)
     m = measure(eng, ring_dev, args, torch, dist, world, S, T, launch_count, local)
     name = "fused" if info["front_end"] == 0 else ("wide" if args.mode == "full" else "default")

@@ -46,6 +46,8 @@ class fm_component(C.Structure):
 FLAG_KEEP_PLANES = 1
 FLAG_NO_FUSED = 2
 FLAG_NO_UMMA = 8
+FLAG_UMMA_APRON = 16
+FLAG_UMMA = 32
 
 # every symbol include/fm_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -70,6 +72,7 @@ SYMBOLS = {
     "fm_debug_planes": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fm_debug_mask": (C.c_int, [_P, C.c_int, _P]),
     "fm_debug_components": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(fm_component), C.POINTER(C.c_int)]),
+    "fm_resize_area": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "fm_launch_count": (C.c_uint64, []),
     "fm_timing_enable": (C.c_int, [_P, C.c_int]),
     "fm_timing_reset": (C.c_int, [_P]),

@@ -40,10 +40,16 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + sources()
+    tmp = LIB + ".tmp.%d" % os.getpid()              # built aside and renamed: a reader never sees a half-written library
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", tmp] + sources()
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    try:
+        subprocess.run(cmd, check=True, cwd=CSRC)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

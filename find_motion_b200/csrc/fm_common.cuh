@@ -51,7 +51,10 @@ struct fm_ctx {
     bool fused;                // K1 fused stencil+background kernel drives the front end
     bool wide_fused;           // wide Gaussian: the vertical pass runs the temporal stage too (k_wide_vt)
     bool umma;                 // blur + temporal stage on tcgen05 tensor cores (k_umma.cu), k <= 97
-    uint8_t *uband;            // band (Toeplitz) operand of the tcgen05 blur
+    uint8_t *uband;            // band (Toeplitz) operand of the tcgen05 blur (apron-plane kernel)
+    uint8_t *uband_f;          // ... of the kernel that reads the BGR frames directly
+    bool umma_direct;          // full-resolution mode with TMA-compatible rows: no gray / apron plane at all
+    int umma_ra;               // apron class of the direct kernel (16: k <= 33, 48: k <= 97)
     uint8_t *gpad;             // [S][Tmax][Hp][Wp] gray plane with the BORDER_REFLECT_101 apron materialised
     int fx, fy;                // integer ratios (mode 2)
     int maxc;
@@ -74,7 +77,6 @@ struct fm_ctx {
     uint32_t *fill;            // [S][Tmax][h][wpr]  dilated threshold with holes filled
     int *any;                  // [S][Tmax][4] range of set pixels: (max y, max h-1-y, max word column j, max wpr-1-j), -1 = none
     int *rawrange;             // [S][Tmax][2] row range of the RAW threshold (written by the temporal kernels)
-    int *heavy;                // [S][Tmax] frame needs the global-memory labelling kernel
     int *ncomp;                // [S][Tmax]
     int *ncounted;             // [S][Tmax]
     fm_component *comps;       // [S][Tmax][maxc]
@@ -138,7 +140,6 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
 int fm_launch_temporal(fm_ctx *c, int T, cudaStream_t st);
 int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 int fm_ccl_configure(fm_ctx *c);
-int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out);
 int fm_launch_masks(fm_ctx *c, int stream, int n_polys, const int *offs, const int *pts_scaled,
                     int npts, cudaStream_t st);
@@ -154,7 +155,10 @@ int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_
 int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
+int fm_launch_resize_bgr(int device, const uint8_t *src_dev, int W, int H, int w, int h, int mode, int fx, int fy,
+                         const ResizeTab &xt, const ResizeTab &yt, uint8_t *dst_dev, cudaStream_t st);
 bool fm_umma_supported(const fm_ctx *c);
+bool fm_umma_preferred(const fm_ctx *c);
 int fm_umma_init(fm_ctx *c, const int *taps);
 size_t fm_umma_bg_doubles(const fm_ctx *c);
 int fm_launch_umma_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);

@@ -133,6 +133,13 @@ static int upload_tab(ResizeTab *d, const HostTab &h) {
     return FM_OK;
 }
 
+namespace {
+struct DevBuf {           // scratch that is released on every return path
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}
+
 // --------------------------------------------------------------------------------------------
 // context
 // --------------------------------------------------------------------------------------------
@@ -140,13 +147,13 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(c->coef); cudaFree(c->wtab); cudaFree(c->uband); cudaFree(c->gpad);
+    cudaFree(c->coef); cudaFree(c->wtab); cudaFree(c->uband); cudaFree(c->uband_f); cudaFree(c->gpad);
     cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
     cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
-    cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
+    cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
     cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->nvalid);
     free(c->nvalid_host);
     fm_ccl_free(&c->ccl);
@@ -271,7 +278,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
         }
     }
     c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);
-    c->umma = !c->fused && fm_umma_supported(c) && !(cfg->flags & FM_FLAG_NO_UMMA);
+    c->umma = !c->fused && fm_umma_supported(c) && !(cfg->flags & FM_FLAG_NO_UMMA) &&
+              ((cfg->flags & FM_FLAG_UMMA) || fm_umma_preferred(c));
     c->wide_fused = !c->fused && !c->umma && fm_wide_fused_supported(c);
     inf.front_end = c->fused ? 0 : (c->resize_mode == 0 ? 1 : 2);
     {
@@ -313,9 +321,8 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     // one memset each per call
     ALLOC(c->rawrange, F * 6 * sizeof(int));
     c->any = c->rawrange + 2 * F;
-    ALLOC(c->ncomp, F * 2 * sizeof(int));
+    ALLOC(c->ncomp, (F * 2 + 4) * sizeof(int));        // + the frame counter of the decision tail
     c->ncounted = c->ncomp + F;
-    ALLOC(c->heavy, F * sizeof(int));
     ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
     ALLOC(c->stats, F * sizeof(fm_frame_stats));
     ALLOC(c->state, (size_t)c->S * sizeof(StreamState));
@@ -331,7 +338,6 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     FM_TRY(cudaMemset(c->bg, 0, bg_doubles * sizeof(double)));
     FM_TRY(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
     FM_TRY(cudaMemset(c->errflag, 0, sizeof(int)));
-    FM_TRY(cudaMemset(c->heavy, 0, F * sizeof(int)));
     // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
     // most w/4 + 2 runs of either polarity; sub-batch sized to <= 8 GB (only the slots of existing runs are ever touched)
     int cap = c->w / 4 + 3;
@@ -446,7 +452,7 @@ extern "C" int fm_process_ragged(fm_ctx *c, const uint8_t *frames, size_t stream
     {   // per-frame result slots of the call: ranges = -1 (nothing set), counters = 0
         const size_t Fmax = (size_t)c->S * c->Tmax;
         FM_CUDA(cudaMemsetAsync(c->rawrange, 0xFF, Fmax * 6 * sizeof(int), st));
-        FM_CUDA(cudaMemsetAsync(c->ncomp, 0, Fmax * 2 * sizeof(int), st));
+        FM_CUDA(cudaMemsetAsync(c->ncomp, 0, (Fmax * 2 + 4) * sizeof(int), st));
     }
     cudaEvent_t *ev = nullptr;
     if (c->timing) {
@@ -656,13 +662,6 @@ extern "C" int fm_get_components(fm_ctx *c, int stream, int t, int max_n, fm_com
     return FM_OK;
 }
 
-namespace {
-struct DevBuf {           // scratch that is released on every return path
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-}
-
 extern "C" int fm_debug_planes(fm_ctx *c, int stream, int t, uint8_t *gray, uint8_t *blur, uint8_t *thresh,
                                double *bg) {
     if (!c) { fm_set_error("null context"); return FM_EINVAL; }
@@ -707,6 +706,41 @@ extern "C" int fm_debug_mask(fm_ctx *c, int stream, uint8_t *mask) {
     int rc = fm_launch_mask_export(c, stream, (uint8_t *)d.p, 0);
     if (rc) return rc;
     FM_CUDA(cudaMemcpy(mask, d.p, c->N, cudaMemcpyDeviceToHost));
+    return FM_OK;
+}
+
+// find_objects' input plane (find_motion.py:703-706): imutils.resize(frame.raw, width=300) = INTER_AREA, BGR out
+extern "C" int fm_resize_area(int device, const uint8_t *bgr_host, int W, int H, int width, uint8_t *out_host, int *out_height) {
+    if (!bgr_host || !out_host || W < 1 || H < 1 || width < 1) { fm_set_error("bad argument"); return FM_EINVAL; }
+    if (width > W) { fm_set_error("width %d > frame width %d: upscaling resize is not supported", width, W); return FM_ERANGE; }
+    int ndev = 0;
+    FM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { fm_set_error("CUDA device %d not present", device); return FM_ECUDA; }
+    FM_CUDA(cudaSetDevice(device));
+    const int h = (int)((double)H * ((double)width / (double)W));            // imutils.resize: int(h * r)
+    if (h < 1) { fm_set_error("resized height is zero"); return FM_ERANGE; }
+    if (out_height) *out_height = h;
+    if (width == W && h == H) { memcpy(out_host, bgr_host, (size_t)W * H * 3); return FM_OK; }
+    const double sx = 1.0 / ((double)width / W), sy = 1.0 / ((double)h / H);
+    const int isx = (int)nearbyint(sx), isy = (int)nearbyint(sy);
+    const bool fast = fabs(sx - isx) < 2.220446049250313e-16 && fabs(sy - isy) < 2.220446049250313e-16;
+    struct Tabs {
+        ResizeTab x{}, y{};
+        ~Tabs() { cudaFree(x.start); cudaFree(x.idx); cudaFree(x.wt); cudaFree(y.start); cudaFree(y.idx); cudaFree(y.wt); }
+    } tb;
+    int rc;
+    if (!fast) {
+        if ((rc = upload_tab(&tb.x, area_tab(W, width)))) return rc;
+        if ((rc = upload_tab(&tb.y, area_tab(H, h)))) return rc;
+    }
+    DevBuf src, dst;
+    FM_CUDA(cudaMalloc(&src.p, (size_t)W * H * 3));
+    FM_CUDA(cudaMalloc(&dst.p, (size_t)width * h * 3));
+    FM_CUDA(cudaMemcpy(src.p, bgr_host, (size_t)W * H * 3, cudaMemcpyHostToDevice));
+    if ((rc = fm_launch_resize_bgr(device, (const uint8_t *)src.p, W, H, width, h, fast ? 2 : 1, isx, isy, tb.x, tb.y,
+                                   (uint8_t *)dst.p, 0)))
+        return rc;
+    FM_CUDA(cudaMemcpy(out_host, dst.p, (size_t)width * h * 3, cudaMemcpyDeviceToHost));
     return FM_OK;
 }
 

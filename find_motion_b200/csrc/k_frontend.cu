@@ -57,7 +57,8 @@ struct K0Params {
     const float *ywt;
     int max_ytaps;
     uint8_t *gray;
-    const int *nvalid;           // [S] real frames of each stream in this call
+    const int *nvalid;           // [S] real frames of each stream in this call (null: every frame)
+    uint8_t *bgr_out;            // [F][h][w][3] resized BGR instead of gray (fm_resize_area: the detector input plane)
 };
 
 #define K0_THREADS 512
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(K0_THREADS) k_resize_gray(K0Params p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int f = blockIdx.y;
     const int s = f / p.T, t = f - s * p.T;
-    if (t >= __ldg(p.nvalid + s)) return;
+    if (p.nvalid && t >= __ldg(p.nvalid + s)) return;
     const int dy = blockIdx.x;
     const uint8_t *src = p.frames + (size_t)s * p.sstride + (size_t)t * p.fstride;
     const int rowbytes = p.W * 3;
@@ -171,9 +172,39 @@ __global__ void __launch_bounds__(K0_THREADS) k_resize_gray(K0Params p) {
         small[i] = (unsigned char)min(max(v, 0), 255);
     }
     __syncthreads();
+    if (p.bgr_out) {
+        uint8_t *o = p.bgr_out + ((size_t)f * p.h + dy) * w3;
+        for (int i = tid; i < w3; i += K0_THREADS) o[i] = small[i];
+        return;
+    }
     uint8_t *g = p.gray + ((size_t)f * p.h + dy) * p.w;
     for (int dx = tid; dx < p.w; dx += K0_THREADS)
         g[dx] = (uint8_t)fm_gray(small[dx * 3], small[dx * 3 + 1], small[dx * 3 + 2]);
+}
+
+// standalone INTER_AREA resize of one BGR frame (device buffers); mode / tables as fm_ctx_create derives them
+int fm_launch_resize_bgr(int device, const uint8_t *src_dev, int W, int H, int w, int h, int mode, int fx, int fy,
+                         const ResizeTab &xt, const ResizeTab &yt, uint8_t *dst_dev, cudaStream_t st) {
+    K0Params p;
+    p.frames = src_dev; p.sstride = 0; p.fstride = 0;
+    p.T = 1; p.W = W; p.H = H; p.w = w; p.h = h;
+    p.mode = mode; p.fx = fx; p.fy = fy;
+    p.xstart = xt.start; p.xidx = xt.idx; p.xwt = xt.wt;
+    p.ystart = yt.start; p.yidx = yt.idx; p.ywt = yt.wt;
+    p.max_ytaps = mode == 1 ? yt.max_taps : fy;
+    p.gray = nullptr; p.nvalid = nullptr; p.bgr_out = dst_dev;
+    const int rowpitch = (W * 3 + 16 + 15) & ~15;
+    const size_t smem = (size_t)K0_GROUPS * rowpitch + (size_t)p.max_ytaps * w * 3 * sizeof(float);
+    if (smem > 220 * 1024) {
+        fm_set_error("resize needs %zu bytes of shared memory (frame too wide / ratio too large)", smem);
+        return FM_ERANGE;
+    }
+    int rc;
+    if ((rc = fm_ensure_smem((const void *)k_resize_gray, smem, device))) return rc;
+    dim3 grid(h, 1);
+    k_resize_gray<<<grid, K0_THREADS, smem, st>>>(p);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,7 +468,7 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         p.xstart = c->xtab.start; p.xidx = c->xtab.idx; p.xwt = c->xtab.wt;
         p.ystart = c->ytab.start; p.yidx = c->ytab.idx; p.ywt = c->ytab.wt;
         p.max_ytaps = c->resize_mode == 1 ? c->ytab.max_taps : c->fy;
-        p.gray = c->gray; p.nvalid = c->nvalid;
+        p.gray = c->gray; p.nvalid = c->nvalid; p.bgr_out = nullptr;
         int rowpitch = (c->W * 3 + 16 + 15) & ~15;
         if (c->resize_mode == 1) {
             // one warp per (frame, destination row, group of <= 32 destination columns)

@@ -357,17 +357,10 @@ __device__ __forceinline__ void collect_row(const CclArgs &a, int lf, int f, int
 // between phases goes through L2: atomics and ld.global.cg).  Only the rows around the set
 // pixels are visited; quiet frames exit at once.
 #define CCL_THREADS 1024
-__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const int *__restrict__ heavy) {
-    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
-    if (heavy && !heavy[f]) return;                 // already labelled by k_ccl_frame_smem
+// all CCL_THREADS threads of the CTA; rows [ylo, yhi] of frame f (scratch slot lf)
+// (not inlined: the rare fallback must not weigh on the register allocation and code size of the shared-memory path)
+__device__ __noinline__ void ccl_frame_global(const CclArgs &a, int lf, int f, int ylo, int yhi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
-    int ylo = 0, yhi = a.h - 1;
-    if (a.rowrange) {
-        int ymax = a.rowrange[4 * f], ymin = a.h - 1 - a.rowrange[4 * f + 1];
-        if (ymax < 0) return;                       // no set pixel in this frame
-        ylo = max(ymin - 1, 0);
-        yhi = min(ymax + 1, a.h - 1);
-    }
     if (threadIdx.x == 0) a.parent[(size_t)lf * (a.slots + 1)] = 0;      // the outside node
     // pass 1: background runs, 4-connected, linked to the outside -> holes
     for (int y = ylo + warp; y <= yhi; y += nw) runs_row<true>(a, a.plane, lf, f, y, lane);
@@ -384,6 +377,85 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const i
     for (int y = ylo + warp; y <= yhi; y += nw) stats_row(a, lf, f, y, lane);
     __syncthreads();
     for (int y = ylo + warp; y <= yhi; y += nw) collect_row(a, lf, f, y, lane);
+}
+
+// decision state machine of one stream over the frames of the call (find_motion.py:665-700, 549-589)
+struct DecideArgs {
+    StreamState *state;
+    fm_frame_stats *stats, *stats_out;
+    const int *nvalid;
+    int *done;                 // frames labelled so far in this call (cleared with the counters)
+    int S, T, total, cache_frames, min_movement_frames;
+};
+
+__device__ __forceinline__ void decide_stream(const DecideArgs &d, const int *ncomp, const int *ncounted, int s) {
+    StreamState st = d.state[s];
+    const int T = d.T;
+    const int Ts = min(T, d.nvalid[s]);           // real frames of this stream in the call (ragged batches)
+    for (int t = Ts; t < T; t++) {
+        fm_frame_stats z = {0, 0, 0, 0, 0, 0, 0, 0};
+        d.stats[s * T + t] = z;
+        if (d.stats_out) d.stats_out[s * T + t] = z;
+    }
+    if (Ts <= 0) return;                        // the stream did not take part: state untouched
+    for (int t = 0; t < Ts; t++) {
+        int f = s * T + t;
+        fm_frame_stats r;
+        r.n_contours = __ldcg(ncomp + f);
+        r.n_counted = __ldcg(ncounted + f);
+        if (st.decay > 0) st.decay -= 1;                       // find_motion.py:672
+        bool movement = r.n_counted > 0;
+        st.counter = movement ? st.counter + r.n_counted : 0;   // :694 per contour, :697-698
+        r.wrote = 0;
+        r.n_flush = 0;
+        if (st.counter >= d.min_movement_frames || st.decay > 0) {   // :555
+            if (movement) {
+                st.decay = d.cache_frames;                      // :559
+                r.n_flush = st.cache_len;                       // :561-570
+                st.cache_len = 0;
+            }
+            r.wrote = 1;                                        // :583
+        } else {
+            st.cache_len = min(st.cache_len + 1, d.cache_frames); // deque(maxlen), :415, :588
+        }
+        r.movement = movement ? 1 : 0;
+        r.movement_counter = st.counter;
+        r.movement_decay = st.decay;
+        r.cache_len = st.cache_len;
+        d.stats[f] = r;
+        if (d.stats_out) d.stats_out[f] = r;
+    }
+    st.has_bg = 1;
+    d.state[s] = st;
+}
+
+// tail of a labelling CTA: the CTA that finishes the last frame of the call runs the decisions of every stream
+// (no separate launch; the counters it reads were written with atomics / before the fence of their CTAs)
+__device__ __forceinline__ void ccl_tail(const CclArgs &a, const DecideArgs &d) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(d.done, 1) == d.total - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int s = threadIdx.x; s < d.S; s += blockDim.x) decide_stream(d, a.ncomp, a.ncounted, s);
+}
+
+__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, DecideArgs d) {
+    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
+    int ylo = 0, yhi = a.h - 1;
+    bool work = true;
+    if (a.rowrange) {
+        int ymax = a.rowrange[4 * f], ymin = a.h - 1 - a.rowrange[4 * f + 1];
+        if (ymax < 0) work = false;                 // no set pixel in this frame
+        ylo = max(ymin - 1, 0);
+        yhi = min(ymax + 1, a.h - 1);
+    }
+    if (work) ccl_frame_global(a, lf, f, ylo, yhi);
+    if (d.done) ccl_tail(a, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -566,7 +638,8 @@ __device__ __forceinline__ void flatten_forest(int *parent, int n) {
     }
 }
 
-__device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restrict__ heavy, unsigned char *csm, int f, int lf,
+// returns false when the frame has more runs than the shared tables hold (nothing has been published then)
+__device__ __forceinline__ bool ccl_frame_lanes(const CclArgs &a, unsigned char *csm, int f, int lf,
                                                 int ylo, int yhi, int jlo, int wprw) {
     const int ww = min(a.w - 32 * jlo, 32 * wprw);           // window width in pixels
     const int nrows = yhi - ylo + 1;
@@ -613,7 +686,7 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
         if (!lane_extract<true>(dil + (size_t)(act ? yr : 0) * pitch, act, yr, 1, bg, &cur_bg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
+    if (overflow) return false;
     const int nbg = cur_bg;
     for (int i = threadIdx.x; i < nbg; i += CCL2_THREADS) run_union<false, true, true>(bg, 1, i, ylo, ww, a.h);
     flatten_forest(bg.parent, nbg + 1);
@@ -644,8 +717,7 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
         if (!lane_extract<false>(fil + (size_t)(act ? yr : 0) * pitch, act, yr, 0, fg, &cur_fg, wsum, ww, wprw)) overflow = 1;
     }
     __syncthreads();
-    if (overflow) { if (threadIdx.x == 0) heavy[f] = 1; return; }
-    if (threadIdx.x == 0) heavy[f] = 0;
+    if (overflow) return false;
     const int total = cur_fg;
     int *area2 = a.area2 + (size_t)lf * a.slots, *bbox = a.bbox + (size_t)lf * a.slots * 4;
     for (int i = threadIdx.x; i < total; i += CCL2_THREADS) {
@@ -703,16 +775,16 @@ __device__ __forceinline__ void ccl_frame_lanes(const CclArgs &a, int *__restric
             a.comps[(size_t)f * a.maxc + slot] = c;
         }
     }
+    return true;
 }
 
-__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
-    extern __shared__ __align__(16) unsigned char csm[];
-    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
-    int ylo = 0, yhi = a.h - 1, jlo = 0, jhi = a.wpr - 1;
+// dilation (optional) + window of frame f; false = quiet frame
+__device__ __forceinline__ bool ccl_window(const CclArgs &a, int f, int &ylo, int &yhi, int &jlo, int &jhi) {
+    ylo = 0; yhi = a.h - 1; jlo = 0; jhi = a.wpr - 1;
     if (a.raw) {
         // ---- 5x5 dilation of the raw threshold bits of this frame (rows within 3 of a pixel above threshold) ----
         const int rmax = a.rawrange[2 * f], rmin = a.h - 1 - a.rawrange[2 * f + 1];
-        if (rmax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }      // quiet frame: rangeout stays (-1, ...)
+        if (rmax < 0) return false;                                        // quiet frame: rangeout stays (-1, ...)
         __shared__ int rng[4];
         if (threadIdx.x < 4) rng[threadIdx.x] = -1;
         __syncthreads();
@@ -735,68 +807,34 @@ __global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, i
         }
         __syncthreads();
         if (threadIdx.x < 4) a.rangeout[4 * f + threadIdx.x] = rng[threadIdx.x];
-        if (rng[0] < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
+        if (rng[0] < 0) return false;
         ylo = max(a.h - 1 - rng[1] - 1, 0);
         yhi = min(rng[0] + 1, a.h - 1);
         jhi = rng[2];
         jlo = a.wpr - 1 - rng[3];
     } else if (a.rowrange) {
         int ymax = a.rowrange[4 * f], ymin = a.h - 1 - a.rowrange[4 * f + 1];
-        if (ymax < 0) { if (threadIdx.x == 0) heavy[f] = 0; return; }
+        if (ymax < 0) return false;
         ylo = max(ymin - 1, 0);
         yhi = min(ymax + 1, a.h - 1);
         jhi = a.rowrange[4 * f + 2];
         jlo = a.wpr - 1 - a.rowrange[4 * f + 3];
     }
-    ccl_frame_lanes(a, heavy, csm, f, lf, ylo, yhi, jlo, jhi - jlo + 1);
+    return true;
 }
 
-// ---------------------------------------------------------------------------------------------
-// decision state machine, one thread per stream, frames in order
-// ---------------------------------------------------------------------------------------------
-__global__ void k_decide(StreamState *__restrict__ state, const int *__restrict__ ncomp,
-                         const int *__restrict__ ncounted, fm_frame_stats *__restrict__ stats,
-                         fm_frame_stats *__restrict__ stats_out, int S, int T, int cache_frames,
-                         int min_movement_frames, const int *__restrict__ nvalid) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    StreamState st = state[s];
-    const int Ts = min(T, nvalid[s]);           // real frames of this stream in the call (ragged batches)
-    for (int t = Ts; t < T; t++) {
-        fm_frame_stats z = {0, 0, 0, 0, 0, 0, 0, 0};
-        stats[s * T + t] = z;
-        if (stats_out) stats_out[s * T + t] = z;
-    }
-    if (Ts <= 0) return;                        // the stream did not take part: state untouched
-    for (int t = 0; t < Ts; t++) {
-        int f = s * T + t;
-        fm_frame_stats r;
-        r.n_contours = ncomp[f];
-        r.n_counted = ncounted[f];
-        if (st.decay > 0) st.decay -= 1;                       // find_motion.py:672
-        bool movement = r.n_counted > 0;
-        st.counter = movement ? st.counter + r.n_counted : 0;   // :694 per contour, :697-698
-        r.wrote = 0;
-        r.n_flush = 0;
-        if (st.counter >= min_movement_frames || st.decay > 0) {   // :555
-            if (movement) {
-                st.decay = cache_frames;                        // :559
-                r.n_flush = st.cache_len;                       // :561-570
-                st.cache_len = 0;
-            }
-            r.wrote = 1;                                        // :583
-        } else {
-            st.cache_len = min(st.cache_len + 1, cache_frames); // deque(maxlen), :415, :588
+__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, DecideArgs d) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
+    int ylo, yhi, jlo, jhi;
+    if (ccl_window(a, f, ylo, yhi, jlo, jhi)) {
+        // frames with more runs than the shared tables hold are labelled with the tables in global memory (whole rows)
+        if (!ccl_frame_lanes(a, csm, f, lf, ylo, yhi, jlo, jhi - jlo + 1)) {
+            __syncthreads();                      // the dilated rows written above are read back through L2
+            ccl_frame_global(a, lf, f, ylo, yhi);
         }
-        r.movement = movement ? 1 : 0;
-        r.movement_counter = st.counter;
-        r.movement_decay = st.decay;
-        r.cache_len = st.cache_len;
-        stats[f] = r;
-        if (stats_out) stats_out[f] = r;
     }
-    st.has_bg = 1;
-    state[s] = st;
+    if (d.done) ccl_tail(a, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -882,10 +920,12 @@ int fm_ccl_configure(fm_ctx *c) {          // fm_ctx_create: fail here, not at t
     return fm_ensure_smem((const void *)k_ccl_frame_smem, smem, c->cfg.device);
 }
 
-// labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane
+// labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane; `use_smem`: tables in shared memory
+// (with the global-memory tables as the in-kernel fallback of frames with too many runs); `d.done` != null: the CTA
+// that finishes the last frame runs the decisions of the call
 static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
-                   int max_area, int *errflag, int *heavy, int T, int t0, int Th, cudaStream_t st,
+                   int max_area, int *errflag, bool use_smem, int T, int t0, int Th, cudaStream_t st, DecideArgs d,
                    const uint32_t *raw = nullptr, const int *rawrange = nullptr, int flatwords = 0) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
@@ -899,30 +939,32 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.bbox = sc.bbox; a.errflag = errflag;
         a.ncomp = ncomp; a.ncounted = ncounted; a.comps = comps; a.maxc = maxc;
         a.min_area = min_area; a.max_area = max_area;
+        a.cache_words = 0;
         size_t smem = 0;
-        if (heavy && ccl_smem_plan(h, wpr, &smem, &a.cache_words)) {
+        if (use_smem && ccl_smem_plan(h, wpr, &smem, &a.cache_words)) {
             int dev = 0;
             FM_CUDA(cudaGetDevice(&dev));
             int rc = fm_ensure_smem((const void *)k_ccl_frame_smem, smem, dev);
             if (rc) return rc;
-            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
-            FM_LAUNCH_CHECK();
-            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
-            FM_LAUNCH_CHECK();
+            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, d);
         } else {
             a.raw = nullptr;
-            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, nullptr);
-            FM_LAUNCH_CHECK();
+            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, d);
         }
+        FM_LAUNCH_CHECK();
     }
     return FM_OK;
 }
 
-// dilation + contours of every frame of a T-frame call (the per-frame result slots -- ranges, counts -- are cleared
-// by fm_process before the front end runs; frames beyond a stream's n_valid keep an empty range and are skipped)
-static int fm_launch_morph_range(fm_ctx *c, int T, cudaStream_t st) {
-    const int t0 = 0, Th = T;
-    const int F = c->S * Th;
+// Dilation + contours + decisions of a T-frame call.  The per-frame result slots (ranges, counts, the frame counter of
+// the decision tail) are cleared by fm_process before the front end runs; frames beyond a stream's n_valid keep an
+// empty range and leave at once.
+int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
+    const int F = c->S * T;
+    DecideArgs d;
+    d.state = c->state; d.stats = c->stats; d.stats_out = stats_out; d.nvalid = c->nvalid;
+    d.done = c->ncomp + 2 * (size_t)c->S * c->Tmax;            // behind the two counter arrays: cleared with them
+    d.S = c->S; d.T = T; d.total = F; d.cache_frames = c->info.cache_frames; d.min_movement_frames = c->info.min_movement_frames;
     size_t smem_plan = 0;
     int cw_plan = 0;
     const bool smem_ok = ccl_smem_plan(c->h, c->wpr, &smem_plan, &cw_plan);
@@ -930,31 +972,18 @@ static int fm_launch_morph_range(fm_ctx *c, int T, cudaStream_t st) {
     // threshold bits of its frame itself; with few frames the grid-wide k_dilate (one warp per row) is faster.
     if (smem_ok && F >= 32)
         return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                       c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st, c->tflat,
+                       c->maxc, c->info.min_area, c->info.max_area, c->errflag, true, T, 0, T, st, d, c->tflat,
                        c->rawrange, c->ntiles * FM_TILE_WORDS);
     int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (c->w % 32 == 0)
         k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                               c->wpr, c->ntiles * FM_TILE_WORDS, T, t0, Th);
+                                                               c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
     else
         k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                                c->wpr, c->ntiles * FM_TILE_WORDS, T, t0, Th);
+                                                                c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
     FM_LAUNCH_CHECK();
     return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                   c->maxc, c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, t0, Th, st);
-}
-
-int fm_launch_decide(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
-    k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(c->state, c->ncomp, c->ncounted, c->stats, stats_out, c->S, T,
-                                                 c->info.cache_frames, c->info.min_movement_frames, c->nvalid);
-    FM_LAUNCH_CHECK();
-    return FM_OK;
-}
-
-int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
-    int rc;
-    if ((rc = fm_launch_morph_range(c, T, st))) return rc;
-    return fm_launch_decide(c, T, st, stats_out);
+                   c->maxc, c->info.min_area, c->info.max_area, c->errflag, smem_ok, T, 0, T, st, d);
 }
 
 // standalone labelling of one host plane (parity tests of the contour stage)
@@ -989,7 +1018,8 @@ int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n,
     dim3 grid((wpr + 63) / 64, h);
     k_u8_to_bits<<<grid, 64>>>(q.d8, q.pl, w, h, wpr);
     FM_LAUNCH_CHECK();
-    rc = ccl_run(q.sc, q.pl, q.fill, nullptr, 1, w, h, wpr, q.cnt, q.cnt + 1, q.comps, maxc, 0, 0, q.cnt + 2, q.cnt + 3, 1, 0, 1, 0);
+    DecideArgs nod{};          // labelling only
+    rc = ccl_run(q.sc, q.pl, q.fill, nullptr, 1, w, h, wpr, q.cnt, q.cnt + 1, q.comps, maxc, 0, 0, q.cnt + 2, true, 1, 0, 1, 0, nod);
     if (rc) return rc;
     FM_CUDA(cudaDeviceSynchronize());
     int hc[3];

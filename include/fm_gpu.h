@@ -55,7 +55,11 @@ typedef struct fm_config {
 
 #define FM_FLAG_KEEP_PLANES 1   /* keep gray/blur planes of the last call for fm_debug_planes */
 #define FM_FLAG_NO_FUSED    2   /* force the generic multi-kernel front end (A/B testing) */
-#define FM_FLAG_NO_UMMA     8   /* wide Gaussian on the mma.sync two-pass path instead of the tcgen05 one-pass kernel (A/B) */
+#define FM_FLAG_UMMA_APRON  16  /* tcgen05 blur through the gray plane with a materialised border apron even when the BGR
+                                   frames could feed the kernel directly (A/B; it is the path of the resize modes) */
+#define FM_FLAG_NO_UMMA     8   /* never take the tcgen05 one-pass Gaussian (k_umma.cu); the mma.sync two-pass kernels instead */
+#define FM_FLAG_UMMA        32  /* take the tcgen05 one-pass Gaussian wherever it applies (3 <= k <= 97, w % 32 == 0); without
+                                   either flag the library picks the faster path for the geometry (measured: DESIGN.md) */
 
 /* Derived parameters, exactly as the reference computes them. */
 typedef struct fm_info {
@@ -173,6 +177,12 @@ int fm_debug_mask(fm_ctx *ctx, int stream, uint8_t *mask);
  * size h*w with findContours(RETR_EXTERNAL)+contourArea+boundingRect semantics. */
 int fm_debug_components(int device, const uint8_t *plane, int w, int h, int max_n,
                         fm_component *out, int *n);
+
+/* The detector input plane of find_objects (find_motion.py:703-706): imutils.resize(frame.raw, width=300), i.e.
+ * cv2.resize(INTER_AREA) of one BGR frame to (width, int(H * width / W)), bit-exact.  Host buffers;
+ * out_host holds width * out_height * 3 bytes.  The detectors themselves stay on the host. */
+int fm_resize_area(int device, const uint8_t *bgr_host, int frame_width, int frame_height, int width,
+                   uint8_t *out_host, int *out_height);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t fm_launch_count(void);

@@ -205,3 +205,15 @@ def test_blur_shapes_that_used_to_take_the_naive_kernels():
     # resize to an odd width (box 111 from 640x480): k = 5 on a 111-pixel plane
     kw = dict(fps=6, box_size=111, blur_scale=20, threshold=6, avg=0.15, min_time=0.3, cache_time=0.5)
     _run(640, 480, 8, 4, kw, seed=720, expect_front_end=2)
+
+
+def test_detector_input_plane_matches_cv2():
+    """N3 (find_motion.py:703-706): imutils.resize(frame.raw, width=300) on the GPU == cv2.resize(INTER_AREA)."""
+    cv2 = pytest.importorskip("cv2")
+    from find_motion_b200 import synth
+    from find_motion_b200.engine import resize_area
+    for W, H, width in ((1920, 1080, 300), (640, 480, 300), (1280, 720, 300), (600, 338, 300), (333, 217, 100), (300, 200, 300)):
+        frame = synth.make_clip(W, H, 1, seed=W + width)[0]
+        want = cv2.resize(frame, (width, int(H * (width / float(W)))), interpolation=cv2.INTER_AREA)
+        got = resize_area(frame, width)
+        assert got.shape == want.shape and (got == want).all(), (W, H, width, int((got != want).sum()))

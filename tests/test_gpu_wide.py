@@ -51,22 +51,22 @@ GEOMETRIES = [
 ]
 
 
-@pytest.mark.parametrize("no_umma", [False, True])
+@pytest.mark.parametrize("umma", [True, False])
 @pytest.mark.parametrize("W,H,bs", GEOMETRIES)
-def test_wide_blur_geometries(W, H, bs, no_umma):
-    """no_umma=False: planes with w % 32 == 0 and k <= 97 take the tcgen05 one-pass kernel (k_umma.cu), the others the
-    mma.sync two-pass kernels; no_umma=True forces the two-pass kernels everywhere."""
+def test_wide_blur_geometries(W, H, bs, umma):
+    """umma=True: planes with w % 32 == 0 and k <= 97 take the tcgen05 one-pass kernel (k_umma.cu), the others the
+    mma.sync two-pass kernels; umma=False: the library's default choice."""
     kw = dict(fps=6, box_size=W, blur_scale=bs, threshold=5, avg=0.2, min_time=0.3, cache_time=0.6,
               mask_areas=[((2, 1), (W // 3, H // 2)), ((W // 2, 0), (W - 1, H // 3), (W // 2, H - 1))])
-    _run(W, H, 9, 4, kw, seed=500 + W, expect_front_end=1, no_umma=no_umma)
+    _run(W, H, 9, 4, kw, seed=500 + W, expect_front_end=1, umma=umma)
 
 
-@pytest.mark.parametrize("no_umma", [False, True])
-def test_wide_blur_two_streams_mixed_masks(no_umma):
+@pytest.mark.parametrize("umma", [True, False])
+def test_wide_blur_two_streams_mixed_masks(umma):
     from find_motion_b200 import synth
     kw = dict(fps=10, box_size=640, blur_scale=20, threshold=8, avg=0.1, min_time=0.2, cache_time=0.4,
               mask_areas=synth.README_MASKS)                  # k = 33
-    _run(640, 360, 10, 5, kw, seed=610, n_streams=2, expect_front_end=1, no_umma=no_umma)
+    _run(640, 360, 10, 5, kw, seed=610, n_streams=2, expect_front_end=1, umma=umma)
 
 
 # tcgen05 kernel: tile grid edges (partial 128 x 128 tiles), every kernel radius class, avg outside [0, 1], resize in front
@@ -81,24 +81,36 @@ UMMA_GEOMETRIES = [
 ]
 
 
+@pytest.mark.parametrize("umma_apron", [False, True])
 @pytest.mark.parametrize("W,H,bs,_", UMMA_GEOMETRIES)
-def test_umma_blur_geometries(W, H, bs, _):
+def test_umma_blur_geometries(W, H, bs, _, umma_apron):
+    """umma_apron=False: the BGR frames feed the tcgen05 kernel directly (TMA ring + gray conversion + mirroring inside the
+    tile) where the geometry allows; True: through the gray plane with a materialised apron (the path of the resize modes)."""
     kw = dict(fps=6, box_size=W, blur_scale=bs, threshold=5, avg=0.2, min_time=0.3, cache_time=0.6,
               mask_areas=[((2, 1), (W // 3, H // 2)), ((W // 2, 0), (W - 1, H // 3), (W // 2, H - 1))])
-    _run(W, H, 6, 4, kw, seed=900 + W, no_fused=True)
+    _run(W, H, 6, 4, kw, seed=900 + W, no_fused=True, umma=True, umma_apron=umma_apron)
 
 
-def test_umma_blur_avg_outside_unit_range_and_k1():
+@pytest.mark.parametrize("W,H,bs", [(1920, 1080, 20), (1920, 1080, 384), (1280, 720, 40), (640, 480, 64), (3840, 2160, 40)])
+def test_umma_direct_full_frames(W, H, bs):
+    """Full frames through the direct kernel, both apron classes (k <= 33 / k <= 97): every tile border case of real sizes."""
+    kw = dict(fps=30, box_size=W, blur_scale=bs, threshold=10, avg=0.1, min_time=0.1, cache_time=0.2,
+              mask_areas=[((0, 0), (100, 100)), ((0, 0), (0, 100), (100, 0)), ((W - 300, H - 200), (W - 1, H - 1))])
+    _run(W, H, 3, 2, kw, seed=950 + W, no_fused=True, umma=True)
+
+
+@pytest.mark.parametrize("umma_apron", [False, True])
+def test_umma_blur_avg_outside_unit_range_and_k1(umma_apron):
     kw = dict(fps=6, box_size=128, blur_scale=9, threshold=6, avg=1.7, min_time=0.3, cache_time=0.5)     # k = 15
-    _run(128, 96, 8, 4, kw, seed=930, no_fused=True)
-    kw = dict(fps=6, box_size=128, blur_scale=128, threshold=6, avg=0.3, min_time=0.3, cache_time=0.5)   # k = 1
-    _run(128, 96, 8, 4, kw, seed=931, no_fused=True)
+    _run(128, 96, 8, 4, kw, seed=930, no_fused=True, umma=True, umma_apron=umma_apron)
+    kw = dict(fps=6, box_size=128, blur_scale=128, threshold=6, avg=0.3, min_time=0.3, cache_time=0.5)   # k = 1: identity blur
+    _run(128, 96, 8, 4, kw, seed=931, no_fused=True, umma=True, umma_apron=umma_apron)
 
 
 def test_umma_blur_after_resize():
     """2x integer resize (960x540 -> 480x270 would not be % 32; 1280x720 -> 640x360 is), k = 33 on the resized plane."""
     kw = dict(fps=8, box_size=640, blur_scale=20, threshold=6, avg=0.15, min_time=0.3, cache_time=0.5)
-    _run(1280, 720, 6, 3, kw, seed=940, expect_front_end=2)
+    _run(1280, 720, 6, 3, kw, seed=940, expect_front_end=2, umma=True)
 
 
 def test_wide_blur_after_resize():
