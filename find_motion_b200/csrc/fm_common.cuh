@@ -77,6 +77,7 @@ struct fm_ctx {
     uint32_t *fill;            // [S][Tmax][h][wpr]  dilated threshold with holes filled
     int *any;                  // [S][Tmax][4] range of set pixels: (max y, max h-1-y, max word column j, max wpr-1-j), -1 = none
     int *rawrange;             // [S][Tmax][2] row range of the RAW threshold (written by the temporal kernels)
+    int *heavy;                // [S][Tmax] frame needs the global-memory labelling kernel
     int *ncomp;                // [S][Tmax]
     int *ncounted;             // [S][Tmax]
     fm_component *comps;       // [S][Tmax][maxc]

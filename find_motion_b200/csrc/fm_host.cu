@@ -153,7 +153,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
     cudaFree(c->maskbits); cudaFree(c->maskflat); cudaFree(c->tflat); cudaFree(c->dil); cudaFree(c->fill);
-    cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
+    cudaFree(c->heavy); cudaFree(c->rawrange); cudaFree(c->ncomp); cudaFree(c->comps); cudaFree(c->stats);      // any / ncounted live inside rawrange / ncomp
     cudaFree(c->state); cudaFree(c->errflag); cudaFree(c->nvalid);
     free(c->nvalid_host);
     fm_ccl_free(&c->ccl);
@@ -323,6 +323,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     c->any = c->rawrange + 2 * F;
     ALLOC(c->ncomp, (F * 2 + 4) * sizeof(int));        // + the frame counter of the decision tail
     c->ncounted = c->ncomp + F;
+    ALLOC(c->heavy, F * sizeof(int));
     ALLOC(c->comps, F * c->maxc * sizeof(fm_component));
     ALLOC(c->stats, F * sizeof(fm_frame_stats));
     ALLOC(c->state, (size_t)c->S * sizeof(StreamState));
@@ -338,6 +339,7 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
     FM_TRY(cudaMemset(c->bg, 0, bg_doubles * sizeof(double)));
     FM_TRY(cudaMemset(c->state, 0, (size_t)c->S * sizeof(StreamState)));
     FM_TRY(cudaMemset(c->errflag, 0, sizeof(int)));
+    FM_TRY(cudaMemset(c->heavy, 0, F * sizeof(int)));
     // contour scratch: a dilated plane has runs >= 3 px separated by >= 1 px, so a row holds at
     // most w/4 + 2 runs of either polarity; sub-batch sized to <= 8 GB (only the slots of existing runs are ever touched)
     int cap = c->w / 4 + 3;

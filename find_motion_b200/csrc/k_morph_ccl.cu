@@ -83,6 +83,62 @@ __device__ __forceinline__ uint32_t dilate_row(const uint32_t *__restrict__ flat
     return anyw;
 }
 
+// The same dilation for a BLOCK of consecutive rows [ya, yb) walked by one warp: the vertical OR slides (one new row per
+// step instead of five loads), the raw rows of the next four steps are requested before the current four are combined
+// (the steps of a row block would otherwise pay one L2 round trip each), and all word columns of a lane (NCH = words per
+// row / 32, rounded up) are carried together so that the +-2 pixel neighbours come from registers.
+template <bool ALIGNED, int NCH>
+__device__ __noinline__ void dilate_rows(const uint32_t *flat, uint32_t *dplane, int ya, int yb, int w, int h, int wpr, int lane,
+                                            int &jmin, int &jmax, int &ymn, int &ymx) {
+    auto raw = [&](int y, int c) -> uint32_t {
+        const int j = lane + 32 * c;
+        if ((unsigned)y >= (unsigned)h || j >= wpr) return 0u;
+        return ALIGNED ? __ldcg(flat + (size_t)y * wpr + j) : flat_row_word(flat, y, j, w, h, wpr);
+    };
+    uint32_t win[NCH][4];            // raw rows y-2 .. y+1 of the row about to be produced
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) win[c][i] = raw(ya - 2 + i, c);
+    for (int y0 = ya; y0 < yb; y0 += 4) {
+        uint32_t nxt[NCH][4];        // raw rows y0+2 .. y0+5: the new row of each of the next four steps
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) nxt[c][i] = raw(y0 + 2 + i, c);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int y = y0 + i;
+            if (y >= yb) break;
+            uint32_t v[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                v[c] = win[c][0] | win[c][1] | win[c][2] | win[c][3] | nxt[c][i];
+                win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = win[c][3]; win[c][3] = nxt[c][i];
+            }
+            uint32_t anyw = 0;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                uint32_t vm = __shfl_up_sync(0xffffffffu, v[c], 1), vp = __shfl_down_sync(0xffffffffu, v[c], 1);
+                const uint32_t pl = c > 0 ? __shfl_sync(0xffffffffu, v[c > 0 ? c - 1 : 0], 31) : 0u;
+                const uint32_t nf = c + 1 < NCH ? __shfl_sync(0xffffffffu, v[c + 1 < NCH ? c + 1 : c], 0) : 0u;
+                if (lane == 0) vm = pl;
+                if (lane == 31) vp = nf;
+                const int j = lane + 32 * c;
+                if (j < wpr) {
+                    uint32_t d = v[c] | (v[c] << 1) | (v[c] << 2) | (v[c] >> 1) | (v[c] >> 2) | (vm >> 31) | (vm >> 30) | (vp << 31) | (vp << 30);
+                    const int rem = w - 32 * j;
+                    if (rem < 32) d &= (1u << rem) - 1u;
+                    dplane[(size_t)y * wpr + j] = d;
+                    anyw |= d;
+                    if (d) { jmax = max(jmax, j); jmin = min(jmin, j); }
+                }
+            }
+            if (__any_sync(0xffffffffu, anyw != 0)) { ymx = max(ymx, y); ymn = min(ymn, y); }
+        }
+    }
+}
+
 // rowrange[4f] = max y with a set pixel (-1: none), [4f+1] = max (h-1-y), [4f+2] = max word column j with a set
 // pixel, [4f+3] = max (wpr-1-j)   (memset 0xFF before)
 template <bool ALIGNED>
@@ -358,8 +414,7 @@ __device__ __forceinline__ void collect_row(const CclArgs &a, int lf, int f, int
 // pixels are visited; quiet frames exit at once.
 #define CCL_THREADS 1024
 // all CCL_THREADS threads of the CTA; rows [ylo, yhi] of frame f (scratch slot lf)
-// (not inlined: the rare fallback must not weigh on the register allocation and code size of the shared-memory path)
-__device__ __noinline__ void ccl_frame_global(const CclArgs &a, int lf, int f, int ylo, int yhi) {
+__device__ __forceinline__ void ccl_frame_global(const CclArgs &a, int lf, int f, int ylo, int yhi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = CCL_THREADS / 32;
     if (threadIdx.x == 0) a.parent[(size_t)lf * (a.slots + 1)] = 0;      // the outside node
     // pass 1: background runs, 4-connected, linked to the outside -> holes
@@ -429,23 +484,16 @@ __device__ __forceinline__ void decide_stream(const DecideArgs &d, const int *nc
     d.state[s] = st;
 }
 
-// tail of a labelling CTA: the CTA that finishes the last frame of the call runs the decisions of every stream
-// (no separate launch; the counters it reads were written with atomics / before the fence of their CTAs)
-__device__ __forceinline__ void ccl_tail(const CclArgs &a, const DecideArgs &d) {
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(d.done, 1) == d.total - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int s = threadIdx.x; s < d.S; s += blockDim.x) decide_stream(d, a.ncomp, a.ncounted, s);
+// decisions of the call, one thread per stream (measured: a "last CTA done" tail inside the labelling kernel and an in-kernel
+// call of the global-memory fallback made the labelling kernel 15 us slower than these two tiny extra launches cost)
+__global__ void k_decide(DecideArgs d, const int *__restrict__ ncomp, const int *__restrict__ ncounted) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < d.S) decide_stream(d, ncomp, ncounted, s);
 }
 
-__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, DecideArgs d) {
+__global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, const int *__restrict__ heavy) {
     const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
+    if (heavy && !heavy[f]) return;                 // already labelled by k_ccl_frame_smem
     int ylo = 0, yhi = a.h - 1;
     bool work = true;
     if (a.rowrange) {
@@ -455,7 +503,6 @@ __global__ void __launch_bounds__(CCL_THREADS, 1) k_ccl_frame(CclArgs a, DecideA
         yhi = min(ymax + 1, a.h - 1);
     }
     if (work) ccl_frame_global(a, lf, f, ylo, yhi);
-    if (d.done) ccl_tail(a, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -792,10 +839,16 @@ __device__ __forceinline__ bool ccl_window(const CclArgs &a, int f, int &ylo, in
         const uint32_t *flat = a.raw + (size_t)f * a.flatwords;
         uint32_t *dplane = a.planeout + (size_t)f * a.h * a.wpr;
         int jmax = -1, jmin = a.wpr, ymx = -1, ymn = a.h;
-        for (int y = max(rmin - 3, 0) + warp; y <= min(rmax + 3, a.h - 1); y += CCL2_WARPS) {
-            const uint32_t anyw = a.aligned ? dilate_row<true>(flat, dplane + (size_t)y * a.wpr, y, a.w, a.h, a.wpr, lane, jmin, jmax)
-                                            : dilate_row<false>(flat, dplane + (size_t)y * a.wpr, y, a.w, a.h, a.wpr, lane, jmin, jmax);
-            if (__any_sync(0xffffffffu, anyw != 0)) { ymx = y; ymn = min(ymn, y); }
+        {   // every warp takes a block of consecutive rows
+            const int y0 = max(rmin - 3, 0), y1 = min(rmax + 3, a.h - 1) + 1;
+            const int B = (y1 - y0 + CCL2_WARPS - 1) / CCL2_WARPS;
+            const int ya = y0 + warp * B, yb = min(ya + B, y1);
+            if (ya < yb) {
+#define FM_DIL(AL, N) dilate_rows<AL, N>(flat, dplane, ya, yb, a.w, a.h, a.wpr, lane, jmin, jmax, ymn, ymx)
+                if (a.aligned) { if (a.wpr <= 32) FM_DIL(true, 1); else if (a.wpr <= 64) FM_DIL(true, 2); else FM_DIL(true, 4); }
+                else { if (a.wpr <= 32) FM_DIL(false, 1); else if (a.wpr <= 64) FM_DIL(false, 2); else FM_DIL(false, 4); }
+#undef FM_DIL
+            }
         }
         jmax = __reduce_max_sync(0xffffffffu, jmax);
         jmin = __reduce_min_sync(0xffffffffu, jmin);
@@ -823,18 +876,14 @@ __device__ __forceinline__ bool ccl_window(const CclArgs &a, int f, int &ylo, in
     return true;
 }
 
-__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, DecideArgs d) {
+__global__ void __launch_bounds__(CCL2_THREADS, 1) k_ccl_frame_smem(CclArgs a, int *__restrict__ heavy) {
     extern __shared__ __align__(16) unsigned char csm[];
     const int lf = blockIdx.x, lg = a.f0 + lf, f = (lg / a.Th) * a.T + a.t0 + lg % a.Th;
     int ylo, yhi, jlo, jhi;
-    if (ccl_window(a, f, ylo, yhi, jlo, jhi)) {
-        // frames with more runs than the shared tables hold are labelled with the tables in global memory (whole rows)
-        if (!ccl_frame_lanes(a, csm, f, lf, ylo, yhi, jlo, jhi - jlo + 1)) {
-            __syncthreads();                      // the dilated rows written above are read back through L2
-            ccl_frame_global(a, lf, f, ylo, yhi);
-        }
-    }
-    if (d.done) ccl_tail(a, d);
+    bool is_heavy = false;
+    // frames with more runs than the shared tables hold are left to k_ccl_frame (tables in global memory)
+    if (ccl_window(a, f, ylo, yhi, jlo, jhi)) is_heavy = !ccl_frame_lanes(a, csm, f, lf, ylo, yhi, jlo, jhi - jlo + 1);
+    if (threadIdx.x == 0) heavy[f] = is_heavy;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -920,12 +969,11 @@ int fm_ccl_configure(fm_ctx *c) {          // fm_ctx_create: fail here, not at t
     return fm_ensure_smem((const void *)k_ccl_frame_smem, smem, c->cfg.device);
 }
 
-// labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane; `use_smem`: tables in shared memory
-// (with the global-memory tables as the in-kernel fallback of frames with too many runs); `d.done` != null: the CTA
-// that finishes the last frame runs the decisions of the call
+// labels frames [0, F) of `plane` (dilated) using `fill` as the hole-filled plane; `heavy` != null: tables in shared memory,
+// frames that overflow them are flagged and labelled by the global-memory kernel that follows
 static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, int *rowrange, int F, int w,
                    int h, int wpr, int *ncomp, int *ncounted, fm_component *comps, int maxc, int min_area,
-                   int max_area, int *errflag, bool use_smem, int T, int t0, int Th, cudaStream_t st, DecideArgs d,
+                   int max_area, int *errflag, int *heavy, int T, int t0, int Th, cudaStream_t st,
                    const uint32_t *raw = nullptr, const int *rawrange = nullptr, int flatwords = 0) {
     for (int f0 = 0; f0 < F; f0 += sc.frames) {
         int nf = F - f0 < sc.frames ? F - f0 : sc.frames;
@@ -941,15 +989,17 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
         a.min_area = min_area; a.max_area = max_area;
         a.cache_words = 0;
         size_t smem = 0;
-        if (use_smem && ccl_smem_plan(h, wpr, &smem, &a.cache_words)) {
+        if (heavy && ccl_smem_plan(h, wpr, &smem, &a.cache_words)) {
             int dev = 0;
             FM_CUDA(cudaGetDevice(&dev));
             int rc = fm_ensure_smem((const void *)k_ccl_frame_smem, smem, dev);
             if (rc) return rc;
-            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, d);
+            k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
+            FM_LAUNCH_CHECK();
+            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);          // idle unless a frame overflowed the shared tables
         } else {
             a.raw = nullptr;
-            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, d);
+            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, nullptr);
         }
         FM_LAUNCH_CHECK();
     }
@@ -961,29 +1011,34 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
 // empty range and leave at once.
 int fm_launch_morph_ccl(fm_ctx *c, int T, cudaStream_t st, fm_frame_stats *stats_out) {
     const int F = c->S * T;
-    DecideArgs d;
-    d.state = c->state; d.stats = c->stats; d.stats_out = stats_out; d.nvalid = c->nvalid;
-    d.done = c->ncomp + 2 * (size_t)c->S * c->Tmax;            // behind the two counter arrays: cleared with them
-    d.S = c->S; d.T = T; d.total = F; d.cache_frames = c->info.cache_frames; d.min_movement_frames = c->info.min_movement_frames;
     size_t smem_plan = 0;
-    int cw_plan = 0;
+    int cw_plan = 0, rc;
     const bool smem_ok = ccl_smem_plan(c->h, c->wpr, &smem_plan, &cw_plan);
     // With enough frames to fill the GPU (one CTA per frame) the shared-memory labelling kernel dilates the raw
     // threshold bits of its frame itself; with few frames the grid-wide k_dilate (one warp per row) is faster.
-    if (smem_ok && F >= 32)
-        return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                       c->maxc, c->info.min_area, c->info.max_area, c->errflag, true, T, 0, T, st, d, c->tflat,
-                       c->rawrange, c->ntiles * FM_TILE_WORDS);
-    int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    if (c->w % 32 == 0)
-        k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                               c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
-    else
-        k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
-                                                                c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
+    if (smem_ok && F >= 32) {
+        rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps, c->maxc,
+                     c->info.min_area, c->info.max_area, c->errflag, c->heavy, T, 0, T, st, c->tflat, c->rawrange,
+                     c->ntiles * FM_TILE_WORDS);
+    } else {
+        int blocks = (F * c->h + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        if (c->w % 32 == 0)
+            k_dilate<true><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
+                                                                   c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
+        else
+            k_dilate<false><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(c->tflat, c->dil, c->any, c->rawrange, F, c->w, c->h,
+                                                                    c->wpr, c->ntiles * FM_TILE_WORDS, T, 0, T);
+        FM_LAUNCH_CHECK();
+        rc = ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps, c->maxc,
+                     c->info.min_area, c->info.max_area, c->errflag, smem_ok ? c->heavy : nullptr, T, 0, T, st);
+    }
+    if (rc) return rc;
+    DecideArgs d;
+    d.state = c->state; d.stats = c->stats; d.stats_out = stats_out; d.nvalid = c->nvalid; d.done = nullptr;
+    d.S = c->S; d.T = T; d.total = F; d.cache_frames = c->info.cache_frames; d.min_movement_frames = c->info.min_movement_frames;
+    k_decide<<<(c->S + 127) / 128, 128, 0, st>>>(d, c->ncomp, c->ncounted);
     FM_LAUNCH_CHECK();
-    return ccl_run(c->ccl, c->dil, c->fill, c->any, F, c->w, c->h, c->wpr, c->ncomp, c->ncounted, c->comps,
-                   c->maxc, c->info.min_area, c->info.max_area, c->errflag, smem_ok, T, 0, T, st, d);
+    return FM_OK;
 }
 
 // standalone labelling of one host plane (parity tests of the contour stage)
@@ -1018,8 +1073,7 @@ int fm_ccl_plane(int device, const uint8_t *plane_host, int w, int h, int max_n,
     dim3 grid((wpr + 63) / 64, h);
     k_u8_to_bits<<<grid, 64>>>(q.d8, q.pl, w, h, wpr);
     FM_LAUNCH_CHECK();
-    DecideArgs nod{};          // labelling only
-    rc = ccl_run(q.sc, q.pl, q.fill, nullptr, 1, w, h, wpr, q.cnt, q.cnt + 1, q.comps, maxc, 0, 0, q.cnt + 2, true, 1, 0, 1, 0, nod);
+    rc = ccl_run(q.sc, q.pl, q.fill, nullptr, 1, w, h, wpr, q.cnt, q.cnt + 1, q.comps, maxc, 0, 0, q.cnt + 2, q.cnt + 3, 1, 0, 1, 0);
     if (rc) return rc;
     FM_CUDA(cudaDeviceSynchronize());
     int hc[3];

@@ -115,7 +115,7 @@ struct UmmaParams {
     do {                                                                                           \
         if (p.prof && (tid == 0 || tid == 992) && blockIdx.x == p.tilesX + 1 && blockIdx.y == 0) { \
             const long long now_ = clock64();                                                      \
-            p.prof[(slot) + (tid ? 16 : 0)] += now_ - prof_t;                                      \
+            prof_acc[(slot) + (tid ? 16 : 0)] += now_ - prof_t;                                    \
             prof_t = now_;                                                                         \
         }                                                                                          \
     } while (0)
@@ -148,45 +148,49 @@ __device__ __forceinline__ void ub_split(uint32_t tD1lane, unsigned char *sLo, u
     }
 }
 
-struct UbEpi {                      // per-thread constants of the epilogue
-    uint32_t M, valid;              // polygon mask / inside-the-image bits of the 16 pixels (bit i = row py + i)
-    uint32_t rowsok;                // rows py + i inside the image (whatever the column)
-    bool wordok;                    // the warp's 32-pixel word column exists
-    int lane;
-};
-
-// epilogue of one frame: 16 rows of one column per thread.  blur = (256 hi + lo + 32768) >> 16 evaluated on packed
-// pairs: u = hi + (lo >> 8) + 128 is exactly (256 hi + lo + 32768) >> 8 and fits 16 bits, blur = u >> 8.
-// FAST: no masked pixel, every pixel inside the image, no parity tap in the warp (warp-uniform).
-// Returns the OR of the warp's threshold words.  twrow = bit-plane word of row py of this frame.
-template <bool SAFE, bool FAST>
-__device__ __forceinline__ uint32_t ub_epilogue(uint32_t tLolane, uint32_t tHilane, double (&bg)[16], const UbEpi &e, bool init,
-                                                const UmmaParams &p, uint32_t *twrow, uint8_t *blur_px) {
+// epilogue of one frame: 16 consecutive pixels of one row per thread (tensor-memory lane = row, columns = x: low-plane sums
+// in columns 0..127, high-plane sums in columns 128..255 of D2).  blur = (256 hi + lo + 32768) >> 16 evaluated on packed pairs:
+// u = hi + (lo >> 8) + 128 is exactly (256 hi + lo + 32768) >> 8 and fits 16 bits, blur = u >> 8.
+// MASKED: the thread has masked pixels (M = polygon mask bits, bit j = pixel j) or a parity tap is requested.
+// Returns the 16 threshold bits (bit j = pixel j).
+template <bool SAFE, bool MASKED>
+__device__ __forceinline__ uint32_t ub_epilogue(uint32_t tLo16, uint32_t tHi16, double (&bg)[16], uint32_t M, bool init, const UmmaParams &p,
+                                                uint8_t *blur_px) {
     uint32_t L[8], Hh[8];
-    ub_ld16p(tLolane, L);
-    ub_ld16p(tHilane, Hh);
+    ub_ld16p(tLo16, L);
+    ub_ld16p(tHi16, Hh);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    uint32_t anyw = 0;
     uint32_t Uu[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) Uu[k] = Hh[k] + __byte_perm(L[k], 0, 0x4341) + 0x00800080u;      // blur of rows 2k, 2k+1 in bytes 1, 3
+    for (int k = 0; k < 8; k++) Uu[k] = Hh[k] + __byte_perm(L[k], 0, 0x4341) + 0x00800080u;      // blur of pixels 2k, 2k+1 in bytes 1, 3
+    if (MASKED && blur_px) {
+        uint4 o;
+        o.x = __byte_perm(__byte_perm(Uu[0], Uu[1], 0x7531), 0, 0x3210);
+        o.x = __byte_perm(Uu[0], Uu[1], 0x7531); o.y = __byte_perm(Uu[2], Uu[3], 0x7531);
+        o.z = __byte_perm(Uu[4], Uu[5], 0x7531); o.w = __byte_perm(Uu[6], Uu[7], 0x7531);
+        uint32_t *ow = &o.x;
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++) {
+            const uint32_t m4 = (M >> (4 * wd)) & 0xFu;
+            ow[wd] &= ~(((m4 * 0x00204081u) & 0x01010101u) * 0xFFu);              // masked pixels -> 0
+        }
+        *reinterpret_cast<uint4 *>(blur_px) = o;
+    }
+    uint32_t bits = 0;
+    const uint32_t nthr2 = ~p.thr2;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const uint32_t U = Uu[k];
 #pragma unroll
         for (int hlf = 0; hlf < 2; hlf++) {
             const int i = 2 * k + hlf;
-            uint32_t sv = __byte_perm(U, 0, hlf ? 0x4443 : 0x4441);
-            if (!FAST) {
-                if (e.M & (1u << i)) sv = 0;                                     // mask_off_areas paints BLACK into blur
-                if (blur_px && (e.valid & (1u << i))) blur_px[(size_t)i * p.w] = (uint8_t)sv;
-            }
-            bool bit;
+            uint32_t sv = __byte_perm(Uu[k], 0, hlf ? 0x4443 : 0x4441);
+            if (MASKED && (M & (1u << i))) sv = 0;                               // mask_off_areas paints BLACK into blur
             if (SAFE) {
                 const double X = __hiloint2double(0x43300000, (int)sv);          // 2^52 + blur
                 if (init) bg[i] = X - 4503599627370496.0;                        // ref_frame = blur.astype(float)
                 const int q = __float_as_int(__fadd_rn(__double2float_rn(bg[i]), 12582912.0f));
-                bit = (uint32_t)(q - p.qoff - (int)sv) > p.thr2;                 // |bg8 - blur| > threshold
+                // bits = 2 bits + (|bg8 - blur| > threshold): q - qoff - blur in [0, 2 thr] unless above the threshold
+                asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits) : "r"((uint32_t)(q - p.qoff - (int)sv)), "r"(nthr2));
                 bg[i] = __fma_rn(bg[i], p.beta, __fma_rn(X, p.alpha, p.nC));     // fma(bg, 1 - a, rn(blur * a))
             } else {
                 const double sd = __hiloint2double(0x43300000, (int)sv) - 4503599627370496.0;
@@ -194,23 +198,26 @@ __device__ __forceinline__ uint32_t ub_epilogue(uint32_t tLolane, uint32_t tHila
                 const float f = fminf(fabsf(__double2float_rn(bg[i])), 255.0f);
                 const int b8 = __float_as_int(__fadd_rn(f, 12582912.0f)) & 0x1FF;
                 const int d = (int)sv - b8;
-                bit = (d < 0 ? -d : d) > p.threshold;
+                bits = 2u * bits + ((d < 0 ? -d : d) > p.threshold ? 1u : 0u);
                 bg[i] = __fma_rn(bg[i], p.beta, __dmul_rn(sd, p.alpha));
             }
-            if (!FAST) bit = bit && (e.valid & (1u << i));
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);               // 32 pixels of row py + i
-            anyw |= word;
-            if (e.lane == 0 && (FAST || (e.wordok && (e.rowsok & (1u << i))))) twrow[(size_t)i * p.wpr] = word;
         }
     }
-    return anyw;
+    return __brev(bits) >> 16;          // pixel 0 was pushed first
 }
 
+// per-frame tail of a thread: epilogue, 16-bit store of the threshold bits, row range of the raw mask
 template <bool SAFE>
-__device__ __forceinline__ uint32_t ub_epilogue_any(uint32_t tLolane, uint32_t tHilane, double (&bg)[16], const UbEpi &e, bool init,
-                                                    const UmmaParams &p, uint32_t *twrow, uint8_t *blur_px, bool fast) {
-    return fast ? ub_epilogue<SAFE, true>(tLolane, tHilane, bg, e, init, p, twrow, blur_px)
-                : ub_epilogue<SAFE, false>(tLolane, tHilane, bg, e, init, p, twrow, blur_px);
+__device__ __forceinline__ void ub_frame_out(uint32_t tLo16, uint32_t tHi16, double (&bg)[16], uint32_t M, bool ok, bool init, bool masked,
+                                             const UmmaParams &p, uint16_t *th16, uint8_t *blur_px, int *rr, int ywarp, int lane) {
+    uint32_t bits = masked ? ub_epilogue<SAFE, true>(tLo16, tHi16, bg, M, init, p, blur_px)
+                           : ub_epilogue<SAFE, false>(tLo16, tHi16, bg, M, init, p, nullptr);
+    if (!ok) bits = 0;
+    if (ok) *th16 = (uint16_t)bits;
+    if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 32 rows hold something
+        atomicMax(rr, min(ywarp + 31, p.h - 1));
+        atomicMax(rr + 1, p.h - 1 - ywarp);
+    }
 }
 
 template <bool SAFE>
@@ -252,10 +259,10 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
     const uint32_t tmem = *tmem_slot;
     const uint32_t tD1 = tmem, tLo = tmem + 256, tHi = tmem + 384;
 
-    // this thread's pixels: column X0 + 32 (warp & 3) + lane, rows Y0 + 16 (warp >> 2) .. + 15
+    // this thread's pixels: row Y0 + 32 (warp & 3) + lane (= its tensor-memory lane in D2), columns X0 + 16 (warp >> 2) .. + 15;
+    // in the split stage the same lane is column 32 (warp & 3) + lane of D1
     const int lq = warp & 3, rg = warp >> 2;
-    const int px = X0 + 32 * lq + lane, py = Y0 + 16 * rg;
-    const bool okx = px < p.w;
+    const int px = X0 + 16 * rg, py = Y0 + 32 * lq + lane;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) + ((((size_t)s * p.tilesX * p.tilesY + tile) * 32 + warp) * 8) * 32 + lane;
     double bg[16];
     if (has_bg) {
@@ -266,26 +273,14 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
             bg[2 * i + 1] = v.y;
         }
     }
-    UbEpi e;                          // mask / validity bits of the 16 pixels (bit i = row py + i)
-    e.M = 0; e.valid = 0; e.rowsok = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int y = py + i;
-        if (y < p.h) {
-            e.rowsok |= 1u << i;
-            if (okx) {
-                e.valid |= 1u << i;
-                e.M |= ((__ldg(p.maskbits + ((size_t)s * p.h + y) * p.wpr + (px >> 5)) >> (px & 31)) & 1u) << i;
-            }
-        }
-    }
-    e.lane = lane;
-    e.wordok = (X0 >> 5) + lq < p.wpr;
-    // warp-uniform fast path: nothing masked, every pixel inside the image, no parity tap
-    const bool fast = __all_sync(0xffffffffu, e.M == 0 && e.valid == 0xFFFFu) && p.blur_out == nullptr;
+    // mask bits of the 16 pixels (bit j = pixel px + j); warp-uniform choice of the masked variant
+    const bool ok = py < p.h && px < p.w;
+    uint32_t M = 0;
+    if (ok) M = (__ldg(p.maskbits + ((size_t)s * p.h + py) * p.wpr + (px >> 5)) >> (px & 31)) & 0xFFFFu;
+    const bool masked = __any_sync(0xffffffffu, M != 0) || p.blur_out != nullptr;
 
     const uint32_t idesc1 = (2u << 4) | ((uint32_t)(UB_IN >> 3) << 17) | ((128u >> 4) << 24);      // S32 += U8 x U8, M128, N224
-    const uint32_t idesc2h = (2u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);        // N64: half of the output rows
+    const uint32_t idesc2 = (2u << 4) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);        // N256: both byte planes
     const uint32_t aBand = usmem(sBand), aGray = usmem(sGray), aLo = usmem(sLo), aHi = usmem(sHi);
     auto issue_tma = [&](int t) {                 // thread 0
         uint64_t *bar = &bars[t & 1];
@@ -310,10 +305,12 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
         issue_tma(0);
         issue_mma1(0);
     }
-    uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords + (size_t)py * p.wpr + (X0 >> 5) + lq;
+    uint16_t *th16 = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * p.T * p.flatwords + (size_t)py * p.wpr) + (px >> 4);
     const uint32_t lanebase = (uint32_t)(32 * lq) << 16;
     const int xl = 32 * lq + lane;
 
+    __shared__ long long prof_acc[32];
+    if (p.prof && tid < 32) prof_acc[tid] = 0;
     long long prof_t = clock64();
     for (int t = 0; t < Ts; t++) {
         ub_mbar_wait(&bars[2], t & 1);            // D1 of frame t is complete (and gray stage t & 1 has been read)
@@ -330,32 +327,22 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
         UB_PROF(4);
         if (tid == 0) {
             UB_FENCE_AFTER();
-            // vertical pass in two halves of 64 output rows: the warps of the first half start their epilogue while the
-            // second half is still being multiplied
+            // vertical pass: A = band (rows = output rows), B = both byte planes (N = 128 low + 128 high columns)
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-#pragma unroll
-                for (int j = 0; j < UB_IN / 32; j++) {
-                    const uint64_t bd = ub_desc_plain(aBand + (UB_BOFF + 64 * half - 32 * j) * 32, 128, 256);
-                    ub_mma(tLo + 64 * half, ub_desc_plain(aLo + 2 * j * 128, 128, UB_YQ * 128), bd, idesc2h, j > 0);
-                    ub_mma(tHi + 64 * half, ub_desc_plain(aHi + 2 * j * 128, 128, UB_YQ * 128), bd, idesc2h, j > 0);
-                }
-                ub_commit(&bars[3 + half]);
-            }
+            for (int j = 0; j < UB_IN / 32; j++)
+                ub_mma(tLo, ub_desc_plain(aBand + (UB_BOFF - 32 * j) * 32, 128, 256), ub_desc_plain(aLo + 2 * j * 128, 128, UB_YQ * 128), idesc2,
+                       j > 0);
+            ub_commit(&bars[3]);
             if (t + 1 < Ts) issue_mma1(t + 1);    // runs on the tensor pipe under the epilogue below
         }
         UB_PROF(5);
-        ub_mbar_wait(&bars[3 + (rg >> 2)], t & 1);
+        ub_mbar_wait(&bars[3], t & 1);
         UB_FENCE_AFTER();
         UB_PROF(6);
         uint8_t *bo = p.blur_out ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
-        const uint32_t anyw = ub_epilogue_any<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, e, t == 0 && !has_bg, p, tw, bo, fast);
-        if (anyw && lane == 0) {                          // this warp's 16 rows hold something
-            int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
-            atomicMax(rr, min(py + 15, p.h - 1));
-            atomicMax(rr + 1, p.h - 1 - py);
-        }
-        tw += p.flatwords;
+        ub_frame_out<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, M, ok, t == 0 && !has_bg, masked, p, th16, bo,
+                           p.rawrange + 2 * ((size_t)s * p.T + t), Y0 + 32 * lq, lane);
+        th16 += 2 * p.flatwords;
         UB_PROF(7);
         UB_FENCE_BEFORE();
         __syncthreads();          // D2 and the byte planes are free for frame t + 1
@@ -366,6 +353,7 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
     for (int i = 0; i < 8; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
     UB_FENCE_BEFORE();
     __syncthreads();
+    if (p.prof && tid < 32 && blockIdx.x == p.tilesX + 1 && blockIdx.y == 0) p.prof[tid] += prof_acc[tid];
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
@@ -456,10 +444,9 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
     const uint32_t tmem = *tmem_slot;
     const uint32_t tD1 = tmem, tLo = tmem + 256, tHi = tmem + 384;
 
-    // this thread's pixels: column X0 + 32 (warp & 3) + lane, rows Y0 + 16 (warp >> 2) .. + 15
+    // this thread's pixels: row Y0 + 32 (warp & 3) + lane (= its tensor-memory lane in D2), columns X0 + 16 (warp >> 2) .. + 15
     const int lq = warp & 3, rg = warp >> 2;
-    const int px = X0 + 32 * lq + lane, py = Y0 + 16 * rg;
-    const bool okx = px < p.w;
+    const int px = X0 + 16 * rg, py = Y0 + 32 * lq + lane;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) + ((((size_t)s * p.tilesX * p.tilesY + tile) * 32 + warp) * 8) * 32 + lane;
     double bg[16];
     if (has_bg) {
@@ -470,26 +457,14 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
             bg[2 * i + 1] = v.y;
         }
     }
-    UbEpi e;                          // mask / validity bits of the 16 pixels (bit i = row py + i)
-    e.M = 0; e.valid = 0; e.rowsok = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int y = py + i;
-        if (y < p.h) {
-            e.rowsok |= 1u << i;
-            if (okx) {
-                e.valid |= 1u << i;
-                e.M |= ((__ldg(p.maskbits + ((size_t)s * p.h + y) * p.wpr + (px >> 5)) >> (px & 31)) & 1u) << i;
-            }
-        }
-    }
-    e.lane = lane;
-    e.wordok = (X0 >> 5) + lq < p.wpr;
-    // warp-uniform fast path: nothing masked, every pixel inside the image, no parity tap
-    const bool fast = __all_sync(0xffffffffu, e.M == 0 && e.valid == 0xFFFFu) && p.blur_out == nullptr;
+    // mask bits of the 16 pixels (bit j = pixel px + j); warp-uniform choice of the masked variant
+    const bool ok = py < p.h && px < p.w;
+    uint32_t M = 0;
+    if (ok) M = (__ldg(p.maskbits + ((size_t)s * p.h + py) * p.wpr + (px >> 5)) >> (px & 31)) & 0xFFFFu;
+    const bool masked = __any_sync(0xffffffffu, M != 0) || p.blur_out != nullptr;
 
     const uint32_t idesc1 = (2u << 4) | ((uint32_t)(G::IN >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc2 = (2u << 4) | ((uint32_t)(UB_T >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (2u << 4) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);        // N256: both byte planes
     const uint32_t aBand = usmem(sBand), aGray = usmem(sGray), aLo = usmem(sLo), aHi = usmem(sHi);
 
     // rows / columns of the gray tile that meet non-zero taps: tile row p <-> image row Y0 - RA + p
@@ -580,7 +555,7 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
     convert(0);
     if (tid == 0) issue_mma1();
 
-    uint32_t *tw = p.tbits + (size_t)s * p.T * p.flatwords + (size_t)py * p.wpr + (X0 >> 5) + lq;
+    uint16_t *th16 = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * p.T * p.flatwords + (size_t)py * p.wpr) + (px >> 4);
     const uint32_t lanebase = (uint32_t)(32 * lq) << 16;
     const int xl = 32 * lq + lane;
     const int yq_lo = p_lo >> 4, yq_hi = (p_hi + 15) >> 4;        // 16-row chunks of the horizontal sums that meet non-zero taps
@@ -595,11 +570,9 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
         if (tid == 0) {
             UB_FENCE_AFTER();
 #pragma unroll
-            for (int j = 0; j < G::KS; j++) {
-                const uint64_t bd = ub_desc_plain(aBand + (G::BOFF - 32 * j) * 32, 128, 256);
-                ub_mma(tLo, ub_desc_plain(aLo + 2 * j * 128, 128, G::NU * 128), bd, idesc2, j > 0);
-                ub_mma(tHi, ub_desc_plain(aHi + 2 * j * 128, 128, G::NU * 128), bd, idesc2, j > 0);
-            }
+            for (int j = 0; j < G::KS; j++)
+                ub_mma(tLo, ub_desc_plain(aBand + (G::BOFF - 32 * j) * 32, 128, 256), ub_desc_plain(aLo + 2 * j * 128, 128, G::NU * 128), idesc2,
+                       j > 0);
             ub_commit(&bars[1]);
         }
         if (t + 1 < Ts) {                         // gray of frame t + 1 while the vertical pass runs
@@ -609,13 +582,9 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
         ub_mbar_wait(&bars[1], t & 1);
         UB_FENCE_AFTER();
         uint8_t *bo = p.blur_out ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
-        const uint32_t anyw = ub_epilogue_any<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, e, t == 0 && !has_bg, p, tw, bo, fast);
-        if (anyw && lane == 0) {
-            int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
-            atomicMax(rr, min(py + 15, p.h - 1));
-            atomicMax(rr + 1, p.h - 1 - py);
-        }
-        tw += p.flatwords;
+        ub_frame_out<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, M, ok, t == 0 && !has_bg, masked, p, th16, bo,
+                           p.rawrange + 2 * ((size_t)s * p.T + t), Y0 + 32 * lq, lane);
+        th16 += 2 * p.flatwords;
         UB_FENCE_BEFORE();
         __syncthreads();
         UB_FENCE_AFTER();
@@ -670,7 +639,7 @@ __global__ void k_bg_export_umma(const double *__restrict__ bg, double *__restri
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const int tx = x / UB_T, ty = y / UB_T, lx = x % UB_T, ly = y % UB_T;
-    const int warp = (lx >> 5) + 4 * (ly >> 4), lane = lx & 31, i = ly & 15;
+    const int warp = (ly >> 5) + 4 * (lx >> 4), lane = ly & 31, i = lx & 15;       // thread = row, 16 consecutive columns
     const size_t base = ((((size_t)s * tilesX * tilesY + (size_t)ty * tilesX + tx) * 32 + warp) * 8) * 32;
     dst[(size_t)y * w + x] = bg[(base + (size_t)(i >> 1) * 32 + lane) * 2 + (i & 1)];
 }

@@ -9,7 +9,7 @@ recording every plane and decision.
 
 It only works where /root/reference exists (the build container).  It is used by
   * tests/golden/make_golden.py   -- to generate the committed golden fixtures, and
-  * tests/test_oracle_vs_reference.py -- skipped when the reference is absent.
+  * tests/test_oracle_vs_cv2.py::test_against_live_reference_loop -- skipped when the reference is absent.
 Nothing in the product package imports it.  It cannot travel to the GPU box.
 """
 from __future__ import annotations

@@ -9,10 +9,11 @@ requirements.txt:5).  The behavioural pin is opencv-python-headless 4.13.0.92 on
 AVX2-capable x86-64 host with cv2.setUseOptimized(True).
 
 Pinning: the reference has no tests or golden vectors of its own.
-This restatement is pinned by (1) tests/test_oracle_vs_reference.py, which runs the *real*
-reference loop (oracle/ref_loader.py) and cv2 stage by stage in the build container, and
-(2) tests/golden/*.npz, traces generated from the real reference by
-tests/golden/make_golden.py and committed, which travel to the GPU box.
+This restatement is pinned by (1) tests/test_oracle_vs_cv2.py, which checks it stage by stage
+against cv2 and (test_against_live_reference_loop) against the *real* reference loop
+(oracle/ref_loader.py) in the build container, and (2) tests/golden/*.json, traces generated from
+the real reference by tests/golden/make_golden.py and committed, which travel to the GPU box
+(tests/test_oracle_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this package.  The product (find_motion_b200/) never does.
