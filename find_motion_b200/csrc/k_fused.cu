@@ -8,7 +8,7 @@
 //   --> vertical pass on the packed lanes in registers (sliding 5-row window)
 //   --> polygon mask --> bg8 = rne(f32(bg)), |blur - bg8| > threshold --> bit-packed mask out
 //   --> bg = fma(bg, 1-alpha, rn(blur*alpha))
-// Each thread keeps the float64 background of its 4 x FT_RPT pixels in registers across all T frames,
+// Each thread keeps the float64 background of its 16 pixels (one row, two 8-pixel segments) in registers across all T frames,
 // so the background costs one 16 B/px HBM round trip per call instead of per frame.
 // Replaces blur_frame + mask_off_areas + find_diff's diff/threshold/accumulateWeighted
 // (find_motion/find_motion.py:487-494, 619-635, 246-257, 651-659).
@@ -70,7 +70,7 @@ struct FusedParams {
     int T, w, h, wpr;           // T = frames per stream of the call
     const int *nvalid;          // [S] real frames of each stream in this call (ragged batches), <= T
     int tilesX, tilesY;
-    double *bg;                 // [S][tiles][8 warps][FT_RPT rows][2 pairs][32 lanes] double2
+    double *bg;                 // [S][tiles][8 warps][8 pairs][32 lanes] double2 (thread-private, coalesced)
     const uint32_t *maskbits;   // [S][h][wpr]
     uint32_t *tbits;            // [S][T][flatwords]  (row-padded == flat because w % 32 == 0)
     size_t flatwords;
@@ -138,74 +138,79 @@ __device__ __forceinline__ uint32_t nibble_transpose8(uint32_t x, int lane) {
     return x;
 }
 
-// One thread: FT_RPT + 4 rows of packed horizontal sums in -> FT_RPT output rows x 4 pixels: vertical pass, mask, threshold
-// bits, background update.
-// INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the thread has masked pixels;
+// One thread: 5 rows of packed horizontal sums in -> ONE output row x 16 pixels (two segments of 8 consecutive pixels, 64
+// pixels apart, so that the 128-bit shared loads of a quarter-warp are contiguous): vertical pass, mask, threshold bits,
+// background update.  The 16 threshold bits of a thread are two bytes of the bit plane: no transposition across lanes.
+// INIT: first frame of a stream (ref_frame = blur.astype(float));  MASKED: the warp has masked pixels (M bit j = pixel j);
 // SH8: k = 5 (taps 1,4,6,4,1 compiled in, final shift 8 done by byte selection).
 template <bool KEEP, bool SAFE, bool INIT, bool MASKED, bool SH8>
 __device__ __forceinline__ uint32_t fused_rows(const uint32_t *shw, double (&bg)[FT_PX], uint32_t M, const FusedParams &p,
-                                               uint8_t *blur_out, int rows_valid) {
-    const int b0 = p.b0, b1 = p.b1, b2 = p.b2;
+                                               uint8_t *blur_out, uint32_t vmask) {
+    const uint32_t b0 = p.b0, b1 = p.b1, b2 = p.b2;
     const int qoff = 0x4B400000 - p.threshold;
     const unsigned nthr2 = ~(2u * (unsigned)p.threshold);
     const double nC = -(4503599627370496.0 * p.alpha);
-    uint32_t win[5][2];
     uint32_t bits = 0;
 #pragma unroll
-    for (int rr = 0; rr < FT_RPT + 4; rr++) {
-        const uint2 hv = *reinterpret_cast<const uint2 *>(shw + rr * FH_WORDS);    // pixels (0,1) and (2,3), 16 bits each
+    for (int seg = 0; seg < 2; seg++) {
+        // rows y-2 .. y+2 of the segment, pixels (0,1) (2,3) (4,5) (6,7) per 128-bit load, 16 bits each; accumulated as they
+        // arrive (outer rows, then the +-1 rows, then the centre) to keep the live registers low
+        const uint32_t *sp = shw + 32 * seg;
+        uint32_t v[4];             // the two pixels of a pair in bits [0,8) and [16,24) (SH8: in bytes 1 and 3)
+        {
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(sp), r4 = *reinterpret_cast<const uint4 *>(sp + 4 * FH_WORDS);
+            const uint32_t rn = SH8 ? 0x00800080u : (uint32_t)p.rnd;
+            if (SH8) { v[0] = r0.x + r4.x + rn; v[1] = r0.y + r4.y + rn; v[2] = r0.z + r4.z + rn; v[3] = r0.w + r4.w + rn; }
+            else { v[0] = b0 * (r0.x + r4.x) + rn; v[1] = b0 * (r0.y + r4.y) + rn; v[2] = b0 * (r0.z + r4.z) + rn; v[3] = b0 * (r0.w + r4.w) + rn; }
+        }
+        {
+            const uint4 r1 = *reinterpret_cast<const uint4 *>(sp + FH_WORDS), r3 = *reinterpret_cast<const uint4 *>(sp + 3 * FH_WORDS);
+            const uint32_t m1 = SH8 ? 4u : (uint32_t)b1;
+            v[0] += m1 * (r1.x + r3.x); v[1] += m1 * (r1.y + r3.y); v[2] += m1 * (r1.z + r3.z); v[3] += m1 * (r1.w + r3.w);
+        }
+        {
+            const uint4 r2 = *reinterpret_cast<const uint4 *>(sp + 2 * FH_WORDS);
+            const uint32_t m2 = SH8 ? 6u : (uint32_t)b2;
+            v[0] += m2 * r2.x; v[1] += m2 * r2.y; v[2] += m2 * r2.z; v[3] += m2 * r2.w;
+        }
+        if (!SH8) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { win[i][0] = win[i + 1][0]; win[i][1] = win[i + 1][1]; }
-        win[4][0] = hv.x;
-        win[4][1] = hv.y;
-        if (rr >= 4) {
-            const int r = rr - 4;          // output row of this thread
-            uint32_t v[2];      // the two pixels of a pair in bits [0,8) and [16,24) (SH8: in bytes 1 and 3)
+            for (int j = 0; j < 4; j++) v[j] = (v[j] >> p.shift) & 0x00FF00FFu;
+        }
+        if (KEEP && (vmask & (1u << seg))) {
+            uint2 o;
+            if (SH8) { o.x = __byte_perm(v[0], v[1], 0x7531); o.y = __byte_perm(v[2], v[3], 0x7531); }
+            else { o.x = __byte_perm(v[0], v[1], 0x6420); o.y = __byte_perm(v[2], v[3], 0x6420); }
+            const uint32_t mk = (M >> (8 * seg)) & 0xFFu;
+            o.x &= ~((((mk & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+            o.y &= ~(((((mk >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+            *reinterpret_cast<uint2 *>(blur_out + 64 * seg) = o;
+        }
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                if (SH8) {
-                    v[j] = (win[0][j] + win[4][j] + 0x00800080u) + 4u * (win[1][j] + win[3][j]) + 6u * win[2][j];
-                } else {
-                    uint32_t a = b0 * (win[0][j] + win[4][j]) + b1 * (win[1][j] + win[3][j]) + b2 * win[2][j] + p.rnd;
-                    v[j] = (a >> p.shift) & 0x00FF00FFu;
-                }
-            }
-            if (KEEP) {
-                if (r < rows_valid) {
-                    uint32_t o = SH8 ? __byte_perm(v[0], v[1], 0x7531)
-                                     : ((v[0] & 0xFF) | ((v[0] >> 16) << 8) | ((v[1] & 0xFF) << 16) | ((v[1] >> 16) << 24));
-                    uint32_t mk = (M >> (4 * r)) & 0xFu;
-                    uint32_t keep = ((mk & 1) ? 0u : 0xFFu) | ((mk & 2) ? 0u : 0xFF00u) | ((mk & 4) ? 0u : 0xFF0000u) |
-                                    ((mk & 8) ? 0u : 0xFF000000u);
-                    *reinterpret_cast<uint32_t *>(blur_out + (size_t)r * p.w) = o & keep;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int idx = 4 * r + c;
-                uint32_t sv = SH8 ? __byte_perm(v[c >> 1], 0, (c & 1) ? 0x4443 : 0x4441)
-                                  : ((c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu));
-                if (MASKED && (M & (1u << idx))) sv = 0;          // mask_off_areas paints BLACK into blur
-                if (SAFE) {
-                    // rn(blur * alpha) without an int -> double conversion (the XU pipe converts 16 lanes/clk/SM):
-                    // X = 2^52 + blur is assembled from its bit pattern, and X * alpha - 2^52 * alpha is exactly
-                    // blur * alpha before the single rounding of the FMA (2^52 * alpha is exact).
-                    const double X = __hiloint2double(0x43300000, (int)sv);
-                    if (INIT) bg[idx] = X - 4503599627370496.0;   // ref_frame = blur.astype(float)
-                    int q = bg8_magic<SAFE>(bg[idx]);
-                    push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);           // |bg8 - blur| > threshold
-                    bg[idx] = __fma_rn(bg[idx], p.beta, __fma_rn(X, p.alpha, nC));
-                } else {
-                    const double sd = u8_to_f64(sv);
-                    if (INIT) bg[idx] = sd;
-                    int q = bg8_magic<SAFE>(bg[idx]);
-                    push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);
-                    bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
-                }
+        for (int c = 0; c < 8; c++) {
+            const int idx = 8 * seg + c;
+            uint32_t sv = SH8 ? __byte_perm(v[c >> 1], 0, (c & 1) ? 0x4443 : 0x4441)
+                              : ((c & 1) ? (v[c >> 1] >> 16) : (v[c >> 1] & 0xFFFFu));
+            if (MASKED && (M & (1u << idx))) sv = 0;          // mask_off_areas paints BLACK into blur
+            if (SAFE) {
+                // rn(blur * alpha) without an int -> double conversion (the XU pipe converts 16 lanes/clk/SM):
+                // X = 2^52 + blur is assembled from its bit pattern, and X * alpha - 2^52 * alpha is exactly
+                // blur * alpha before the single rounding of the FMA (2^52 * alpha is exact).
+                const double X = __hiloint2double(0x43300000, (int)sv);
+                if (INIT) bg[idx] = X - 4503599627370496.0;   // ref_frame = blur.astype(float)
+                int q = bg8_magic<SAFE>(bg[idx]);
+                push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);           // |bg8 - blur| > threshold
+                bg[idx] = __fma_rn(bg[idx], p.beta, __fma_rn(X, p.alpha, nC));
+            } else {
+                const double sd = u8_to_f64(sv);
+                if (INIT) bg[idx] = sd;
+                int q = bg8_magic<SAFE>(bg[idx]);
+                push_gt(bits, (unsigned)(q - qoff - (int)sv), nthr2);
+                bg[idx] = __fma_rn(bg[idx], p.beta, __dmul_rn(sd, p.alpha));
             }
         }
     }
-    return __brev(bits) >> (32 - FT_PX);      // the first pixel was pushed first: bit idx = pixel 4r+c
+    return __brev(bits) >> (32 - FT_PX);      // the first pixel was pushed first: bit idx = pixel idx
 }
 
 template <bool KEEP, bool SAFE>
@@ -226,8 +231,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     const int Ts = min(p.T, __ldg(p.nvalid + s));            // frames of this stream that are real
     if (Ts <= 0) return;
 
-    // this thread's pixels: columns x0 + 4*lane .. +3, rows y0 + FT_RPT*warp .. +FT_RPT-1
-    const int px = x0 + 4 * lane, py = y0 + FT_RPT * warp;
+    // this thread's pixels: row y0 + tid / 8, columns x0 + 8 (tid % 8) .. + 7 and the same 64 pixels further right
+    const int trow = tid >> 3, xg = tid & 7;
+    const int px = x0 + 8 * xg, py = y0 + trow;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) +
                    ((((size_t)s * p.tilesX * p.tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32 + lane;
     double bg[FT_PX];
@@ -239,18 +245,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
             bg[2 * i + 1] = v.y;
         }
     }
-    // polygon mask bits of the 32 pixels (bit 4r+c), loaded once per call
+    // polygon mask bits of the 16 pixels (bit j = pixel j of the first segment, bit 8 + j of the second), loaded once per call
     uint32_t M = 0;
-    if (px < w) {
-#pragma unroll
-        for (int r = 0; r < FT_RPT; r++) {
-            int y = py + r;
-            if (y < h) {
-                uint32_t mw = __ldg(p.maskbits + ((size_t)s * h + y) * p.wpr + (px >> 5));
-                M |= ((mw >> (px & 31)) & 0xFu) << (4 * r);
-            }
-        }
-    }
+    const bool okA = py < h && px < w, okB = py < h && px + 64 < w;
+    const uint32_t vmask = (okA ? 1u : 0u) | (okB ? 2u : 0u);
+    if (okA) M = (__ldg(p.maskbits + ((size_t)s * h + py) * p.wpr + (px >> 5)) >> (px & 31)) & 0xFFu;
+    if (okB) M |= ((__ldg(p.maskbits + ((size_t)s * h + py) * p.wpr + ((px + 64) >> 5)) >> (px & 31)) & 0xFFu) << 8;
+    const bool wmasked = __any_sync(0xffffffffu, M != 0);       // warp-uniform choice of the masked variant
     // TMA pipeline: frame t+1 lands in the other stage while frame t is being processed
     const int cx = (x0 * 3) / 4 - 4, cy = y0 - 2;        // box origin in (u32 column, row); OOB is zero-filled
     if (tid == 0) {
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         mbar_expect_tx(&bars[0], RAW_BYTES);
         tma_load_4d(raw, &tmap, &bars[0], cx, cy, 0, s);
     }
-    uint32_t *tw = p.tbits + ((size_t)s * p.T) * p.flatwords;
+    // the thread's two bytes of the bit plane (row py, pixels px .. px+7 and px+64 .. px+71)
+    uint8_t *tb = reinterpret_cast<uint8_t *>(p.tbits + ((size_t)s * p.T) * p.flatwords + (size_t)py * p.wpr) + (px >> 3);
     // B fragments of the horizontal pass (constant): the banded tap matrix for the two 8-column output blocks
     // of a 32-byte window.  Output column n of block nb is gray byte 4 + 16 j + 8 nb + n of its row, window
     // byte k is gray byte 16 j + k, so the tap index is k - n - 8 nb - 2 (taps b0 b1 b2 b1 b0).
@@ -290,7 +292,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     const uint32_t sg_lane = smem_u32(sg) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * (FG_WORDS * 4) + 16 * warp + 16 * (lane >> 4);
     uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * warp + (lane & 3);
 
-    uint32_t pend = 0;
     for (int t = 0; t < Ts; t++) {
         // No barrier here: every thread that gets this far has passed the second barrier of frame t-1, i.e. all
         // conversions out of raw stage (t+1)&1 (frame t-1) and all reads of the gray plane are complete.
@@ -302,15 +303,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
         // ---- staged BGR -> gray bytes in shared memory (tile + halo) ----
         {
             // the staged rows are dense (pitch 432 B = 36 groups of 4 pixels = 12 B, the first at byte 4 because the
-            // TMA box must start 16 B aligned) and so are the gray rows (36 words): group u is raw + 4 + 12 u -> sg[u].
+            // TMA box must start 16 B aligned in global memory -- a box at x0 * 3 - 12 raises "illegal instruction") and
+            // so are the gray rows (36 words): group u is raw + 4 + 12 u -> sg[u].
             const unsigned char *rs = raw + (t & 1) * RAW_STAGE + 4;
             // two units (8 pixels, 24 bytes -> 2 gray words) per step: half the address arithmetic and loop control
 #pragma unroll
             for (int i = 0; i < (FG_ROWS * FG_WORDS / 2 + FUSED_THREADS - 1) / FUSED_THREADS; i++) {
                 int u = tid + i * FUSED_THREADS;
                 if (u < FG_ROWS * FG_WORDS / 2) {
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rs + u * 24);
-                    const uint32_t g0 = gray4(q[0], q[1], q[2]), g1 = gray4(q[3], q[4], q[5]);
+                    // 24 bytes at byte 4 (mod 8) of the stage: 4 + 8 + 8 + 4
+                    const unsigned char *q = rs + u * 24;
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(q), a5 = *reinterpret_cast<const uint32_t *>(q + 20);
+                    const uint2 a12 = *reinterpret_cast<const uint2 *>(q + 4), a34 = *reinterpret_cast<const uint2 *>(q + 12);
+                    const uint32_t g0 = gray4(a0, a12.x, a12.y), g1 = gray4(a34.x, a34.y, a5);
                     *reinterpret_cast<uint2 *>(sg + 2 * u) = make_uint2(g0, g1);
                 }
             }
@@ -361,45 +366,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
             }
         }
         __syncthreads();
-        // ---- vertical pass on packed pairs, sliding 5-row window, then the temporal update ----
-        const uint32_t *sgw = sh + (FT_RPT * warp) * FH_WORDS + 2 * lane;
+        // ---- vertical pass on packed pairs (5 rows x 16 pixels per thread), then the temporal update ----
+        const uint32_t *sgw = sh + trow * FH_WORDS + 4 * xg;
+        asm volatile("" : "+r"(M));        // opaque per frame: keeps the 16 single-bit tests of M from being hoisted (and spilled)
         uint8_t *bo = KEEP ? p.blur_out + (((size_t)s * p.T + t) * h + py) * w + px : nullptr;
-        const bool okx = px < w;
         uint32_t bits;
-        if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        else if (M) bits = fused_rows<KEEP, SAFE, false, true, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        else if (p.shift == 8) bits = fused_rows<KEEP, SAFE, false, false, true>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        else bits = fused_rows<KEEP, SAFE, false, false, false>(sgw, bg, M, p, bo, okx ? h - py : 0);
-        // ---- 8 lanes x FT_RPT rows of nibbles -> one 32-pixel word per lane, coalesced store ----
-#if FT_RPT == 4
-        // a thread has 4 rows: two frames share one transpose (rows 0-3 = frame t-1, rows 4-7 = frame t)
-        if (!(t & 1) && t + 1 < Ts) {
-            pend = bits;
-        } else {
-            const bool two = t & 1;
-            uint32_t word = nibble_transpose8(two ? (pend | (bits << 16)) : bits, lane);
-            const int rsel = lane & 7;
-            const int y = py + (rsel & 3);
-            const int xw = (x0 >> 5) + (lane >> 3);
-            const bool mine = two || rsel < 4;
-            uint32_t *dst = tw + (size_t)y * p.wpr + xw;
-            if (two && rsel < 4) dst -= p.flatwords;
-            if (mine && y < h && xw < p.wpr) *dst = word;
-        }
-#else
-        uint32_t word = nibble_transpose8(bits, lane);
-        {
-            int y = py + (lane & 7);
-            int xw = (x0 >> 5) + (lane >> 3);
-            if (y < h && xw < p.wpr) tw[(size_t)y * p.wpr + xw] = word;
-        }
-#endif
-        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's FT_RPT rows hold something
+        if (t == 0 && !has_bg) bits = fused_rows<KEEP, SAFE, true, true, false>(sgw, bg, M, p, bo, vmask);
+        else if (wmasked) bits = p.shift == 8 ? fused_rows<KEEP, SAFE, false, true, true>(sgw, bg, M, p, bo, vmask)
+                                              : fused_rows<KEEP, SAFE, false, true, false>(sgw, bg, M, p, bo, vmask);
+        else if (p.shift == 8) bits = fused_rows<KEEP, SAFE, false, false, true>(sgw, bg, M, p, bo, vmask);
+        else bits = fused_rows<KEEP, SAFE, false, false, false>(sgw, bg, M, p, bo, vmask);
+        // ---- two bytes of the bit plane per thread ----
+        if (!okA) bits = 0;
+        if (!okB) bits &= 0xFFu;
+        if (okA) tb[0] = (uint8_t)bits;
+        if (okB) tb[8] = (uint8_t)(bits >> 8);
+        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 4 rows hold something
             int *rr = p.rawrange + 2 * ((size_t)s * p.T + t);
-            atomicMax(rr, min(py + FT_RPT - 1, h - 1));
-            atomicMax(rr + 1, h - 1 - py);
+            atomicMax(rr, min(y0 + 4 * warp + 3, h - 1));
+            atomicMax(rr + 1, h - 1 - (y0 + 4 * warp));
         }
-        tw += p.flatwords;
+        tb += 4 * p.flatwords;
     }
 #pragma unroll
     for (int i = 0; i < FT_PX / 2; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
@@ -412,8 +399,9 @@ __global__ void k_bg_export_fused(const double *__restrict__ bg, double *__restr
     if (x >= w) return;
     int tx = x / FT_W, ty = y / FT_H, tile = ty * tilesX + tx;
     int lx = x - tx * FT_W, ly = y - ty * FT_H;
-    int warp = ly / FT_RPT, r = ly % FT_RPT, lane = lx >> 2, c = lx & 3;
-    int idx = 4 * r + c;           // pixel index inside the thread
+    int tid = ly * 8 + ((lx & 63) >> 3);           // thread = row, two 8-pixel segments 64 pixels apart
+    int warp = tid >> 5, lane = tid & 31;
+    int idx = 8 * (lx >> 6) + (lx & 7);            // pixel index inside the thread
     size_t base = ((((size_t)s * tilesX * tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32;
     dst[(size_t)y * w + x] = bg[(base + (size_t)(idx >> 1) * 32 + lane) * 2 + (idx & 1)];
 }

@@ -453,32 +453,44 @@ __device__ __forceinline__ void decide_stream(const DecideArgs &d, const int *nc
         if (d.stats_out) d.stats_out[s * T + t] = z;
     }
     if (Ts <= 0) return;                        // the stream did not take part: state untouched
-    for (int t = 0; t < Ts; t++) {
-        int f = s * T + t;
-        fm_frame_stats r;
-        r.n_contours = __ldcg(ncomp + f);
-        r.n_counted = __ldcg(ncounted + f);
-        if (st.decay > 0) st.decay -= 1;                       // find_motion.py:672
-        bool movement = r.n_counted > 0;
-        st.counter = movement ? st.counter + r.n_counted : 0;   // :694 per contour, :697-698
-        r.wrote = 0;
-        r.n_flush = 0;
-        if (st.counter >= d.min_movement_frames || st.decay > 0) {   // :555
-            if (movement) {
-                st.decay = d.cache_frames;                      // :559
-                r.n_flush = st.cache_len;                       // :561-570
-                st.cache_len = 0;
-            }
-            r.wrote = 1;                                        // :583
-        } else {
-            st.cache_len = min(st.cache_len + 1, d.cache_frames); // deque(maxlen), :415, :588
+    for (int tc = 0; tc < Ts; tc += 16) {
+        // the counts of 16 frames first (independent loads: one L2 round trip per chunk instead of one per frame)
+        int nco[16], ncd[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const bool in = tc + i < Ts;
+            nco[i] = in ? __ldcg(ncomp + s * T + tc + i) : 0;
+            ncd[i] = in ? __ldcg(ncounted + s * T + tc + i) : 0;
         }
-        r.movement = movement ? 1 : 0;
-        r.movement_counter = st.counter;
-        r.movement_decay = st.decay;
-        r.cache_len = st.cache_len;
-        d.stats[f] = r;
-        if (d.stats_out) d.stats_out[f] = r;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (tc + i >= Ts) break;
+            const int f = s * T + tc + i;
+            fm_frame_stats r;
+            r.n_contours = nco[i];
+            r.n_counted = ncd[i];
+            if (st.decay > 0) st.decay -= 1;                       // find_motion.py:672
+            bool movement = r.n_counted > 0;
+            st.counter = movement ? st.counter + r.n_counted : 0;   // :694 per contour, :697-698
+            r.wrote = 0;
+            r.n_flush = 0;
+            if (st.counter >= d.min_movement_frames || st.decay > 0) {   // :555
+                if (movement) {
+                    st.decay = d.cache_frames;                      // :559
+                    r.n_flush = st.cache_len;                       // :561-570
+                    st.cache_len = 0;
+                }
+                r.wrote = 1;                                        // :583
+            } else {
+                st.cache_len = min(st.cache_len + 1, d.cache_frames); // deque(maxlen), :415, :588
+            }
+            r.movement = movement ? 1 : 0;
+            r.movement_counter = st.counter;
+            r.movement_decay = st.decay;
+            r.cache_len = st.cache_len;
+            d.stats[f] = r;
+            if (d.stats_out) d.stats_out[f] = r;
+        }
     }
     st.has_bg = 1;
     d.state[s] = st;

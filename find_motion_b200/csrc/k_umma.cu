@@ -165,7 +165,6 @@ __device__ __forceinline__ uint32_t ub_epilogue(uint32_t tLo16, uint32_t tHi16, 
     for (int k = 0; k < 8; k++) Uu[k] = Hh[k] + __byte_perm(L[k], 0, 0x4341) + 0x00800080u;      // blur of pixels 2k, 2k+1 in bytes 1, 3
     if (MASKED && blur_px) {
         uint4 o;
-        o.x = __byte_perm(__byte_perm(Uu[0], Uu[1], 0x7531), 0, 0x3210);
         o.x = __byte_perm(Uu[0], Uu[1], 0x7531); o.y = __byte_perm(Uu[2], Uu[3], 0x7531);
         o.z = __byte_perm(Uu[4], Uu[5], 0x7531); o.w = __byte_perm(Uu[6], Uu[7], 0x7531);
         uint32_t *ow = &o.x;
@@ -339,7 +338,7 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_blur(const __grid_consta
         ub_mbar_wait(&bars[3], t & 1);
         UB_FENCE_AFTER();
         UB_PROF(6);
-        uint8_t *bo = p.blur_out ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
+        uint8_t *bo = (p.blur_out && ok) ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
         ub_frame_out<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, M, ok, t == 0 && !has_bg, masked, p, th16, bo,
                            p.rawrange + 2 * ((size_t)s * p.T + t), Y0 + 32 * lq, lane);
         th16 += 2 * p.flatwords;
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(UB_THREADS, 1) k_umma_fused(const __grid_const
         }
         ub_mbar_wait(&bars[1], t & 1);
         UB_FENCE_AFTER();
-        uint8_t *bo = p.blur_out ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
+        uint8_t *bo = (p.blur_out && ok) ? p.blur_out + (((size_t)s * p.T + t) * p.h + py) * p.w + px : nullptr;
         ub_frame_out<SAFE>(tLo + lanebase + 16 * rg, tHi + lanebase + 16 * rg, bg, M, ok, t == 0 && !has_bg, masked, p, th16, bo,
                            p.rawrange + 2 * ((size_t)s * p.T + t), Y0 + 32 * lq, lane);
         th16 += 2 * p.flatwords;
