@@ -21,20 +21,20 @@
 #include "fm_common.cuh"
 
 #define FT_W 128
-#ifndef FT_RPT
-#define FT_RPT 4           // rows per thread (a warp owns FT_RPT rows x 128 columns)
+#ifndef FT_H
+#define FT_H 32            // tile height; a thread owns one row x 16 pixels, a warp 4 rows x 128 columns
 #endif
-#define FT_H (8 * FT_RPT)  // tile height
-#define FT_PX (4 * FT_RPT) // pixels (and float64 background values) per thread
+#define FT_PX 16           // pixels (and float64 background values) per thread
+#define FUSED_WARPS (FT_H / 4)
 #define FG_WORDS 36        // gray words per shared row: cols x0-4 .. x0+139 (18 units of 8 pixels)
 #define FG_ROWS (FT_H + 4) // rows y0-2 .. y0+FT_H+1
 #define FH_MB ((FG_ROWS + 15) / 16)     // 16-row blocks of the tensor-core pass
 #define FH_ROWS (16 * FH_MB)            // rows of the shared planes (the rows past FG_ROWS are scratch: no row guards)
 #ifndef FUSED_MIN_CTAS
-#define FUSED_MIN_CTAS (FT_RPT == 4 ? 4 : 2)
+#define FUSED_MIN_CTAS (1024 / (8 * FT_H))      // 64 registers per thread: 1024 resident threads per SM
 #endif
 #define FH_WORDS 68         // packed horizontal sums per shared row: 64 pixel pairs + 4 (bank spread for the D-fragment stores)
-#define FUSED_THREADS 256
+#define FUSED_THREADS (8 * FT_H)
 #define RAW_PITCH 432      // bytes per staged BGR row: bytes x0*3-16 .. x0*3+415 (TMA box of 108 u32)
 #define RAW_BYTES (RAW_PITCH * FG_ROWS)                 // bytes one TMA box delivers
 #define RAW_STAGE ((RAW_BYTES + 127) / 128 * 128)        // stage stride (TMA destinations are 128 B aligned)
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     const int trow = tid >> 3, xg = tid & 7;
     const int px = x0 + 8 * xg, py = y0 + trow;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) +
-                   ((((size_t)s * p.tilesX * p.tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32 + lane;
+                   ((((size_t)s * p.tilesX * p.tilesY + tile) * FUSED_WARPS + warp) * (FT_PX / 2)) * 32 + lane;
     double bg[FT_PX];
     if (has_bg) {
 #pragma unroll
@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     }
     // A-fragment row addresses of LDSM.x4 (lane L supplies row L&7 of matrix L>>3; matrices: rows 0-7 / 8-15 of
     // bytes 0-15, then of bytes 16-31) and D-fragment store positions
-    const uint32_t sg_lane = smem_u32(sg) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * (FG_WORDS * 4) + 16 * warp + 16 * (lane >> 4);
-    uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * warp + (lane & 3);
+    const int hwin = warp & 7;                                  // the warp's 16-column window of the horizontal pass
+    const uint32_t sg_lane = smem_u32(sg) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * (FG_WORDS * 4) + 16 * hwin + 16 * (lane >> 4);
+    uint32_t *sh_lane = sh + (lane >> 2) * FH_WORDS + 8 * hwin + (lane & 3);
 
     for (int t = 0; t < Ts; t++) {
         // No barrier here: every thread that gets this far has passed the second barrier of frame t-1, i.e. all
@@ -348,21 +349,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
                         sg[(ry + 2) * FG_WORDS + ux + 1];
             }
         }
-        // ---- horizontal pass on the tensor cores: warp = one 16-column window, FH_MB blocks of 16 rows ----
+        // ---- horizontal pass on the tensor cores: warp = one 16-column window, every (FUSED_WARPS / 8)-th block of 16 rows ----
         {
-            uint32_t a[FH_MB][4];
+            constexpr int MBS = FUSED_WARPS / 8;                 // warps per window
+            constexpr int NMB = (FH_MB + MBS - 1) / MBS;         // blocks per warp (the last may not exist for every warp)
+            const int mb0 = warp >> 3;
+            uint32_t a[NMB][4];
 #pragma unroll
-            for (int mb = 0; mb < FH_MB; mb++) ldsm_x4(sg_lane + mb * (16 * FG_WORDS * 4), a[mb][0], a[mb][1], a[mb][2], a[mb][3]);
+            for (int i = 0; i < NMB; i++)
+                if (MBS == 1 || mb0 + i * MBS < FH_MB) ldsm_x4(sg_lane + (mb0 + i * MBS) * (16 * FG_WORDS * 4), a[i][0], a[i][1], a[i][2], a[i][3]);
 #pragma unroll
-            for (int mb = 0; mb < FH_MB; mb++) {
-                int d0[4], d1[4];
-                imma_u8(d0, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[0][0], bfr[0][1]);
-                imma_u8(d1, a[mb][0], a[mb][1], a[mb][2], a[mb][3], bfr[1][0], bfr[1][1]);
-                uint32_t *o = sh_lane + mb * (16 * FH_WORDS);
-                o[0] = __byte_perm(d0[0], d0[1], 0x5410);
-                o[4] = __byte_perm(d1[0], d1[1], 0x5410);
-                o[8 * FH_WORDS] = __byte_perm(d0[2], d0[3], 0x5410);
-                o[8 * FH_WORDS + 4] = __byte_perm(d1[2], d1[3], 0x5410);
+            for (int i = 0; i < NMB; i++) {
+                if (MBS == 1 || mb0 + i * MBS < FH_MB) {
+                    int d0[4], d1[4];
+                    imma_u8(d0, a[i][0], a[i][1], a[i][2], a[i][3], bfr[0][0], bfr[0][1]);
+                    imma_u8(d1, a[i][0], a[i][1], a[i][2], a[i][3], bfr[1][0], bfr[1][1]);
+                    uint32_t *o = sh_lane + (mb0 + i * MBS) * (16 * FH_WORDS);
+                    o[0] = __byte_perm(d0[0], d0[1], 0x5410);
+                    o[4] = __byte_perm(d1[0], d1[1], 0x5410);
+                    o[8 * FH_WORDS] = __byte_perm(d0[2], d0[3], 0x5410);
+                    o[8 * FH_WORDS + 4] = __byte_perm(d1[2], d1[3], 0x5410);
+                }
             }
         }
         __syncthreads();
@@ -402,7 +409,7 @@ __global__ void k_bg_export_fused(const double *__restrict__ bg, double *__restr
     int tid = ly * 8 + ((lx & 63) >> 3);           // thread = row, two 8-pixel segments 64 pixels apart
     int warp = tid >> 5, lane = tid & 31;
     int idx = 8 * (lx >> 6) + (lx & 7);            // pixel index inside the thread
-    size_t base = ((((size_t)s * tilesX * tilesY + tile) * 8 + warp) * (FT_PX / 2)) * 32;
+    size_t base = ((((size_t)s * tilesX * tilesY + tile) * FUSED_WARPS + warp) * (FT_PX / 2)) * 32;
     dst[(size_t)y * w + x] = bg[(base + (size_t)(idx >> 1) * 32 + lane) * 2 + (idx & 1)];
 }
 
