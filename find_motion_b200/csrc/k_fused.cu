@@ -80,7 +80,30 @@ struct FusedParams {
     double alpha, beta;
     uint8_t *gray_out, *blur_out;   // [S][T][h][w], only with KEEP
     int *rawrange;                  // [S][T][2] (max y, max h-1-y) of rows with pixels above threshold
+    uint4 bfr[32];                  // per lane: B fragments of the horizontal pass (fused_bfr)
 };
+
+// B fragments of the horizontal pass (constant per call): the banded tap matrix for the two 8-column output blocks of a
+// 32-byte window.  Output column n of block nb is gray byte 4 + 16 j + 8 nb + n of its row, window byte k is gray byte
+// 16 j + k, so the tap index is k - n - 8 nb - 2 (taps b0 b1 b2 b1 b0).  Lane = 4 g + tq holds bytes k = 16 r + 4 tq + i of
+// column n = g: words (nb, r) = (0,0) (0,1) (1,0) (1,1).
+static void fused_bfr(FusedParams &p) {
+    for (int lane = 0; lane < 32; lane++) {
+        const int g = lane >> 2, tq = lane & 3;
+        uint32_t v[4];
+        for (int nb = 0; nb < 2; nb++)
+            for (int r = 0; r < 2; r++) {
+                uint32_t x = 0;
+                for (int i = 0; i < 4; i++) {
+                    const int idx = 16 * r + 4 * tq + i - g - 8 * nb - 2;
+                    const int tap = (idx == 2) ? p.b2 : (idx == 1 || idx == 3) ? p.b1 : (idx == 0 || idx == 4) ? p.b0 : 0;
+                    x |= (uint32_t)tap << (8 * i);
+                }
+                v[2 * nb + r] = x;
+            }
+        p.bfr[lane] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
 
 __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
     // 4 BGR pixels in 3 words -> 4 gray bytes.  Y = (3735 B + 19235 G + 9798 R + 16384) >> 15 computed as
@@ -221,9 +244,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     uint32_t *sh = sg + FH_ROWS * FG_WORDS;                                  // [FH_ROWS][FH_WORDS] packed horizontal sums
     uint64_t *bars = reinterpret_cast<uint64_t *>(sh + FH_ROWS * FH_WORDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
+    const int s = blockIdx.z;
+    const int tx = blockIdx.x, ty = blockIdx.y, tile = ty * p.tilesX + tx;
     const int x0 = tx * FT_W, y0 = ty * FT_H;
     const int w = p.w, h = p.h;
     const bool border = (x0 == 0) || (x0 + FT_W >= w) || (y0 == 0) || (y0 + FT_H >= h);
@@ -267,25 +289,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS) k_fused(const _
     }
     // the thread's two bytes of the bit plane (row py, pixels px .. px+7 and px+64 .. px+71)
     uint8_t *tb = reinterpret_cast<uint8_t *>(p.tbits + ((size_t)s * p.T) * p.flatwords + (size_t)py * p.wpr) + (px >> 3);
-    // B fragments of the horizontal pass (constant): the banded tap matrix for the two 8-column output blocks
-    // of a 32-byte window.  Output column n of block nb is gray byte 4 + 16 j + 8 nb + n of its row, window
-    // byte k is gray byte 16 j + k, so the tap index is k - n - 8 nb - 2 (taps b0 b1 b2 b1 b0).
+    // B fragments of the horizontal pass (constant, prepared by the host: fused_bfr)
     uint32_t bfr[2][2];
     {
-        const int g = lane >> 2, tq = lane & 3;
-#pragma unroll
-        for (int nb = 0; nb < 2; nb++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int idx = 16 * r + 4 * tq + i - g - 8 * nb - 2;
-                    const int tap = (idx == 2) ? p.b2 : (idx == 1 || idx == 3) ? p.b1 : (idx == 0 || idx == 4) ? p.b0 : 0;
-                    v |= (uint32_t)tap << (8 * i);
-                }
-                bfr[nb][r] = v;
-            }
+        const uint4 b = p.bfr[lane];
+        bfr[0][0] = b.x; bfr[0][1] = b.y; bfr[1][0] = b.z; bfr[1][1] = b.w;
+        // opaque: otherwise the compiler re-reads the (lane-indexed, hence serialised) constant bank in every frame
+        asm volatile("" : "+r"(bfr[0][0]), "+r"(bfr[0][1]), "+r"(bfr[1][0]), "+r"(bfr[1][1]));
     }
     // A-fragment row addresses of LDSM.x4 (lane L supplies row L&7 of matrix L>>3; matrices: rows 0-7 / 8-15 of
     // bytes 0-15, then of bytes 16-31) and D-fragment store positions
@@ -479,7 +489,8 @@ int fm_launch_fused(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fst
     p.rawrange = c->rawrange;
     const bool keep = (c->cfg.flags & FM_FLAG_KEEP_PLANES) != 0;
     const bool safe = p.alpha >= 0.0 && p.alpha <= 1.0 && p.threshold >= 0;
-    dim3 grid(p.tilesX * p.tilesY, c->S);
+    fused_bfr(p);
+    dim3 grid(p.tilesX, p.tilesY, c->S);
     int rc;
     if ((rc = fm_ensure_smem((const void *)k_fused<true, true>, FUSED_SMEM, c->cfg.device))) return rc;
     if ((rc = fm_ensure_smem((const void *)k_fused<true, false>, FUSED_SMEM, c->cfg.device))) return rc;
