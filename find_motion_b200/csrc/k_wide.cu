@@ -90,7 +90,7 @@ int fm_wide_init(fm_ctx *c, const int *taps) {
     {   // shared-memory needs of the three kernels, checked when the context is created
         const size_t smh = (size_t)32 * g.pitch + (size_t)(4 * g.Sh + 3) * 256;
         const size_t smv = (size_t)4 * (4 + g.Sv - 1) * 2 * WV_COLS * 16 + (size_t)2 * g.Sv * 512;
-        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512;
+        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512 + WV_ROWS * 16;
         if (smh > 200 * 1024 || smv > 200 * 1024 || smt > 200 * 1024) {
             fm_set_error("Gaussian kernel %d too wide for the tensor-core blur (%zu / %zu / %zu bytes of shared memory)", c->k,
                          smh, smv, smt);
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(128, 4) k_wide_v(const uint4 *__restrict__ plo
     const int per = NGt * 2 * WV_COLS;                                        // 16-byte chunks per plane and stage
     uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][32 slots]
     uint4 *tab = sB + 4 * per;                                                // [2 Sv][32]
+    uint4 *sT = tab + 2 * Sv * 32;                                            // [128 rows] 16 blur bytes
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int f = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, XS = blockIdx.x * (WV_COLS * WV_NT), G0 = Y0 >> 5;
     for (int i = tid; i < 2 * Sv * 32; i += 128) tab[i] = __ldg(tabg + i);
@@ -427,32 +428,36 @@ struct WideVtParams {
     double alpha, beta;
 };
 
-// 4 pixels of one row: lo / hi plane sums -> masked blur bytes -> threshold bits (bit j = pixel j), background update
-template <bool INIT>
-__device__ __forceinline__ uint32_t wt_temporal4(const int (&lo)[4], const int (&hi)[4], uint32_t keep, double (&bg)[4],
-                                                 int qoff, uint32_t nthr2, double alpha, double beta, double nC,
-                                                 uint32_t &blur4) {
-    uint32_t v[4];
+// 16 consecutive pixels of one row (blur bytes q, unmasked): polygon mask, threshold bits (bit j = pixel j), background update.
+// MASKED: the warp has masked pixels (M bit j = pixel j) or the parity tap is on; INIT: first frame of the stream.
+template <bool INIT, bool MASKED>
+__device__ __forceinline__ uint32_t wt_temporal16(uint4 q, uint32_t M, double (&bg)[16], int qoff, uint32_t nthr2, double alpha,
+                                                  double beta, double nC, uint8_t *blur_px) {
+    uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+    if (MASKED) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = (uint32_t)(hi[j] * 256 + lo[j]);           // blur = byte 2 (rounding constant in lo)
-    // mask_off_areas paints BLACK into blur: keep has 0x00 bytes at the masked pixels
-    blur4 = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410) & keep;
+        for (int k = 0; k < 4; k++) w4[k] &= ~(((((M >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);   // BLACK into blur
+        if (blur_px) *reinterpret_cast<uint4 *>(blur_px) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
     uint32_t bits = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t sv = __byte_perm(blur4, 0, 0x4440 + j);
+    for (int i = 0; i < 16; i++) {
+        const uint32_t sv = __byte_perm(w4[i >> 2], 0, 0x4440 + (i & 3));
         const double X = __hiloint2double(0x43300000, (int)sv);                     // 2^52 + blur
-        if (INIT) bg[j] = X - 4503599627370496.0;
-        const int q = __float_as_int(__fadd_rn(__double2float_rn(bg[j]), 12582912.0f));
-        asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits) : "r"((uint32_t)(q - qoff - (int)sv)), "r"(nthr2));
-        bg[j] = __fma_rn(bg[j], beta, __fma_rn(X, alpha, nC));
+        if (INIT) bg[i] = X - 4503599627370496.0;
+        const int qq = __float_as_int(__fadd_rn(__double2float_rn(bg[i]), 12582912.0f));
+        asm("{\n .reg .u32 t;\n add.cc.u32 t, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(bits) : "r"((uint32_t)(qq - qoff - (int)sv)), "r"(nthr2));
+        bg[i] = __fma_rn(bg[i], beta, __fma_rn(X, alpha, nC));
     }
-    return __brev(bits) >> 28;       // bit j = pixel j
+    return __brev(bits) >> 16;       // bit j = pixel j
 }
 
 // grid: (w / 16, ceil(h / 128), S), 128 threads.
-// dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 16 columns * 16 B  +  2 Sv * 512
-__global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
+// dynamic smem: 2 stages * 2 planes * (4 + Sv - 1) groups * 2 halves * 16 columns * 16 B  +  2 Sv * 512  +  128 rows * 16 B
+// The accumulators leave the tensor cores as 4 rows x 4 pixels per thread; the blur bytes go through a 2 KB shared tile so that
+// the temporal stage sees ONE row x 16 pixels per thread (the mapping of K1): no lane shuffles, one 16-bit store of the
+// threshold bits and a quarter of the per-row overhead.
+__global__ void __launch_bounds__(128, 5) k_wide_vt(WideVtParams p) {
     extern __shared__ __align__(16) unsigned char wsm[];
     const int Sv = p.Sv, w = p.w, h = p.h, NGa = p.NGa, T = p.T;
     const int Ts = min(T, __ldg(p.nvalid + blockIdx.z));                      // real frames of this stream (ragged batches)
@@ -461,6 +466,7 @@ __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
     const int per = NGt * 2 * WT_COLS;                                        // 16-byte chunks per plane and stage
     uint4 *sB = reinterpret_cast<uint4 *>(wsm);                               // [stage][plane][NGt][half][16 slots]
     uint4 *tab = sB + 4 * per;                                                // [2 Sv][32]
+    uint4 *sT = tab + 2 * Sv * 32;                                            // [128 rows] 16 blur bytes
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int s = blockIdx.z, Y0 = blockIdx.y * WV_ROWS, X0 = blockIdx.x * WT_COLS, G0 = Y0 >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -493,31 +499,30 @@ __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
         const int col = 4 * (n >> 1) + 2 * (mi >> 1) + (n & 1);
         boff = ((mi & 1) * WT_COLS + wt_slot(col)) * 16;
     }
-    // this thread's pixels: rows Y0 + 32 wq + 16 mt + 8 hr + g, columns X0 + 4 t4 .. + 3 (pixel j: block j >> 1, e = j & 1)
-    const int yb = Y0 + 32 * wq + g, xb = X0 + 4 * t4;
-    uint32_t keep[4];                                                         // byte masks of the rows: 0x00 = masked pixel
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int y = yb + 16 * (r >> 1) + 8 * (r & 1);
-        const uint32_t m = y < h ? (__ldg(p.maskbits + ((size_t)s * h + y) * p.wpr + (xb >> 5)) >> (xb & 31)) & 0xFu : 0u;
-        keep[r] = ~(((m * 0x00204081u) & 0x01010101u) * 0xFFu);
-    }
+    // accumulator fragment of this thread: rows 32 wq + 16 mt + 8 hr + g of the tile, columns 4 t4 .. + 3 (pixel j: block j >> 1,
+    // e = j & 1); temporal stage of this thread: row Y0 + 32 wq + lane, columns X0 .. X0 + 15
+    uint32_t *sTw = reinterpret_cast<uint32_t *>(sT) + (32 * wq + g) * 4 + t4;
+    const uint4 *sTr = sT + 32 * wq + lane;
+    const int y = Y0 + 32 * wq + lane;
+    uint32_t M = 0;                                                           // polygon mask bits of the 16 pixels
+    if (y < h) M = (__ldg(p.maskbits + ((size_t)s * h + y) * p.wpr + (X0 >> 5)) >> (X0 & 31)) & 0xFFFFu;
+    const bool masked = __any_sync(0xffffffffu, M != 0) || p.blur_out != nullptr;
     const bool has_bg = p.state[s].has_bg != 0;
     double2 *bgt = reinterpret_cast<double2 *>(p.bg) +
                    ((((size_t)s * p.tilesY + blockIdx.y) * p.tilesX + blockIdx.x) * 4 + wq) * 8 * 32 + lane;
-    double bg[4][4];
+    double bg[16];
     if (has_bg) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const double2 v = bgt[i * 32];
-            bg[i >> 1][2 * (i & 1)] = v.x;
-            bg[i >> 1][2 * (i & 1) + 1] = v.y;
+            bg[2 * i] = v.x;
+            bg[2 * i + 1] = v.y;
         }
     }
     const int qoff = 0x4B400000 - p.threshold;
     const uint32_t nthr2 = ~(2u * (uint32_t)p.threshold);
     const double nC = -(4503599627370496.0 * p.alpha);
-    uint16_t *tw = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * T * p.flatwords) + (size_t)2 * (X0 >> 5) + ((X0 >> 4) & 1);
+    uint16_t *tw = reinterpret_cast<uint16_t *>(p.tbits + (size_t)s * T * p.flatwords) + (size_t)y * p.wpr * 2 + (size_t)2 * (X0 >> 5) + ((X0 >> 4) & 1);
     for (int t = 0; t < Ts; t++) {
         if (t + 1 < Ts) {
             issue(t + 1);
@@ -547,29 +552,27 @@ __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
         step(0, std::true_type());
 #pragma unroll 1
         for (int sg = 1; sg < Sv; sg++) step(sg, std::false_type());
-        // ---- temporal stage on the thread's 4 rows x 4 pixels ----
-        bool anyb = false;
+        // ---- blur bytes of the fragment -> shared tile (blur = byte 2 of 256 hi + lo, rounding constant already in lo) ----
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int mt = r >> 1, hr = r & 1;
-            const int y = yb + 16 * mt + 8 * hr;
-            int lo[4], hi[4];
+            uint32_t v[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { lo[j] = acc[0][mt][j >> 1][2 * hr + (j & 1)]; hi[j] = acc[1][mt][j >> 1][2 * hr + (j & 1)]; }
-            uint32_t blur4;
-            uint32_t nib = (t == 0 && !has_bg)
-                               ? wt_temporal4<true>(lo, hi, keep[r], bg[r], qoff, nthr2, p.alpha, p.beta, nC, blur4)
-                               : wt_temporal4<false>(lo, hi, keep[r], bg[r], qoff, nthr2, p.alpha, p.beta, nC, blur4);
-            if (y >= h) nib = 0;
-            // the 4 lanes of a row: 16 pixels -> one 16-bit store
-            uint32_t v = nib << (4 * t4);
-            v |= __shfl_xor_sync(0xffffffffu, v, 1);
-            v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t4 == 0 && y < h) tw[(size_t)y * p.wpr * 2] = (uint16_t)v;
-            anyb |= v != 0;
-            if (p.blur_out && y < h) *reinterpret_cast<uint32_t *>(p.blur_out + (((size_t)s * T + t) * h + y) * w + xb) = blur4;
+            for (int j = 0; j < 4; j++) v[j] = (uint32_t)(acc[1][mt][j >> 1][2 * hr + (j & 1)] * 256 + acc[0][mt][j >> 1][2 * hr + (j & 1)]);
+            sTw[(16 * mt + 8 * hr) * 4] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
         }
-        if (__any_sync(0xffffffffu, anyb) && lane == 0) {       // this warp's 32 rows hold something
+        __syncwarp();              // the 32 rows of a warp are produced and consumed by the same warp
+        const uint4 q = *sTr;
+        // ---- temporal stage: one row x 16 pixels per thread ----
+        uint8_t *bo = (p.blur_out && y < h) ? p.blur_out + (((size_t)s * T + t) * h + y) * w + X0 : nullptr;
+        asm volatile("" : "+r"(M));        // opaque per frame: keeps the single-bit tests of M from being hoisted
+        uint32_t bits;
+        if (t == 0 && !has_bg) bits = wt_temporal16<true, true>(q, M, bg, qoff, nthr2, p.alpha, p.beta, nC, bo);
+        else if (masked) bits = wt_temporal16<false, true>(q, M, bg, qoff, nthr2, p.alpha, p.beta, nC, bo);
+        else bits = wt_temporal16<false, false>(q, M, bg, qoff, nthr2, p.alpha, p.beta, nC, nullptr);
+        if (y >= h) bits = 0;
+        if (y < h) *tw = (uint16_t)bits;
+        if (__any_sync(0xffffffffu, bits != 0) && lane == 0) {       // this warp's 32 rows hold something
             int *rr = p.rawrange + 2 * ((size_t)s * T + t);
             atomicMax(rr, min(Y0 + 32 * wq + 31, h - 1));
             atomicMax(rr + 1, h - 1 - (Y0 + 32 * wq));
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(128, 4) k_wide_vt(WideVtParams p) {
         __syncthreads();       // every warp is done with this stage before the loads of frame t + 2 overwrite it
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) bgt[i * 32] = make_double2(bg[i >> 1][2 * (i & 1)], bg[i >> 1][2 * (i & 1) + 1]);
+    for (int i = 0; i < 8; i++) bgt[i * 32] = make_double2(bg[2 * i], bg[2 * i + 1]);
 }
 
 // tiled background of k_wide_vt -> row-major float64 plane
@@ -587,11 +590,10 @@ __global__ void k_bg_export_wide(const double *__restrict__ bg, double *__restri
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const int tx = x / WT_COLS, ty = y / WV_ROWS, lx = x % WT_COLS, ly = y % WV_ROWS;
-    const int wq = ly >> 5, l32 = ly & 31, mt = l32 >> 4, hr = (l32 >> 3) & 1, g = l32 & 7;
-    const int t4 = lx >> 2, j = lx & 3, lane = 4 * g + t4, r = 2 * mt + hr;
-    const int i = 2 * r + (j >> 1);                                // double2 index of the thread
+    const int wq = ly >> 5, lane = ly & 31;                        // thread = row, 16 consecutive columns
+    const int i = lx >> 1, j = lx & 1;                             // double2 index of the thread, component
     const size_t base = ((((size_t)s * tilesY + ty) * tilesX + tx) * 4 + wq) * 8 * 32;
-    dst[(size_t)y * w + x] = bg[(base + (size_t)i * 32 + lane) * 2 + (j & 1)];
+    dst[(size_t)y * w + x] = bg[(base + (size_t)i * 32 + lane) * 2 + j];
 }
 
 bool fm_wide_fused_supported(const fm_ctx *c) {
@@ -668,7 +670,7 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
     }
     FM_LAUNCH_CHECK();
     if (c->wide_fused) {
-        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512;
+        const size_t smt = (size_t)4 * (4 + g.Sv - 1) * 2 * WT_COLS * 16 + (size_t)2 * g.Sv * 512 + WV_ROWS * 16;
         if ((rc = fm_ensure_smem((const void *)k_wide_vt, smt, c->cfg.device))) return rc;
         WideVtParams p;
         p.plo = reinterpret_cast<const uint4 *>(plo); p.phi = reinterpret_cast<const uint4 *>(phi); p.tabg = tabv;
