@@ -48,9 +48,10 @@ def parse_args():
     ap.add_argument("--size", default="1920x1080", help="frame size WxH (the headline metric is 1080p)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic clips (0 = one per stream); "
                     "streams reuse them round-robin (large-batch sweeps)")
-    ap.add_argument("--front-end", default="auto", choices=["auto", "stencil", "umma", "umma-apron", "mma-sync"],
+    ap.add_argument("--front-end", default="auto", choices=["auto", "stencil", "umma", "umma-apron", "mma-sync", "warp-resize"],
                     help="A/B of the front-end kernels: stencil = k_fused (k <= 5), umma = tcgen05 kernel fed by the BGR frames, "
-                         "umma-apron = tcgen05 kernel through the apron plane, mma-sync = the two-pass mma.sync Gaussian")
+                         "umma-apron = tcgen05 kernel through the apron plane, mma-sync = the two-pass mma.sync Gaussian, "
+                         "warp-resize = default mode with the warp-per-destination-row INTER_AREA kernels instead of the row-per-lane one")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary regimes (k=97, default mode)")
@@ -378,7 +379,7 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     fe = {"auto": {}, "stencil": {}, "umma": dict(no_fused=True, umma=True), "umma-apron": dict(no_fused=True, umma=True, umma_apron=True),
-          "mma-sync": dict(no_fused=True, no_umma=True)}[args.front_end]
+          "mma-sync": dict(no_fused=True, no_umma=True), "warp-resize": dict(no_rows=True)}[args.front_end]
     eng = MotionEngine(W, H, n_streams=S, max_frames=T, device=local, **fe, **kw)
     info = dict(eng.info, w=eng.w, h=eng.h)
     m = measure(eng, ring_dev, args, torch, dist, world, S, T, launch_count, local)

@@ -65,6 +65,7 @@ struct fm_ctx {
     int *g4start, *g4n, *g4off;   // x taps regrouped in 4-pixel groups with zero-weight padding (k_resize_gray_g4)
     float4 *g4w;
     int g4max;                    // most tap groups of any destination column
+    struct RowsPlan *rows;        // plan of the row-per-lane resize kernel (k_resize_rows.cu); null: not applicable
     // planes
     uint8_t *gray;             // [S][Tmax][h][w]
     uint16_t *hor;             // horizontal pass: u16 [S][Tmax][h][w] (naive) or the low/high byte planes of k_wide.cu
@@ -158,6 +159,10 @@ size_t fm_fused_bg_doubles(const fm_ctx *c);
 int fm_launch_bg_export_fused(fm_ctx *c, int stream, double *dst_dev, cudaStream_t st);
 int fm_launch_resize_bgr(int device, const uint8_t *src_dev, int W, int H, int w, int h, int mode, int fx, int fy,
                          const ResizeTab &xt, const ResizeTab &yt, uint8_t *dst_dev, cudaStream_t st);
+int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt, const int *ystart, const int *yidx);
+void fm_rows_free(fm_ctx *c);
+bool fm_rows_usable(const fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride);
+int fm_launch_resize_rows(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 bool fm_umma_supported(const fm_ctx *c);
 bool fm_umma_preferred(const fm_ctx *c);
 int fm_umma_init(fm_ctx *c, const int *taps);

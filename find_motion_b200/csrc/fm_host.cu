@@ -149,6 +149,7 @@ extern "C" int fm_ctx_destroy(fm_ctx *c) {
     cudaDeviceSynchronize();
     cudaFree(c->coef); cudaFree(c->wtab); cudaFree(c->uband); cudaFree(c->uband_f); cudaFree(c->gpad);
     cudaFree(c->g4start); cudaFree(c->g4n); cudaFree(c->g4off); cudaFree(c->g4w);
+    fm_rows_free(c);
     cudaFree(c->xtab.start); cudaFree(c->xtab.idx); cudaFree(c->xtab.wt);
     cudaFree(c->ytab.start); cudaFree(c->ytab.idx); cudaFree(c->ytab.wt);
     cudaFree(c->gray); cudaFree(c->hor); cudaFree(c->blur); cudaFree(c->bg);
@@ -274,7 +275,10 @@ extern "C" int fm_ctx_create(const fm_config *cfg, fm_ctx **out) {
                 if ((rc = upload(&c->g4off, g4o))) return fail(rc);
                 if ((rc = upload(&c->g4w, g4w))) return fail(rc);
             }
-            if ((rc = upload_tab(&c->ytab, area_tab(c->H, c->h)))) return fail(rc);
+            HostTab yt = area_tab(c->H, c->h);
+            if ((rc = upload_tab(&c->ytab, yt))) return fail(rc);
+            if ((rc = fm_rows_plan(c, xt.start.data(), xt.idx.data(), xt.wt.data(), yt.start.data(), yt.idx.data())))
+                return fail(rc);
         }
     }
     c->fused = fm_fused_supported(c) && !(cfg->flags & FM_FLAG_NO_FUSED);

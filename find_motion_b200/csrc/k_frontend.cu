@@ -470,7 +470,11 @@ int fm_launch_frontend(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t 
         p.max_ytaps = c->resize_mode == 1 ? c->ytab.max_taps : c->fy;
         p.gray = c->gray; p.nvalid = c->nvalid; p.bgr_out = nullptr;
         int rowpitch = (c->W * 3 + 16 + 15) & ~15;
-        if (c->resize_mode == 1) {
+        if (c->resize_mode == 1 && fm_rows_usable(c, frames, sstride, fstride)) {
+            // one source row per lane, TMA-staged (k_resize_rows.cu)
+            int rc;
+            if ((rc = fm_launch_resize_rows(c, frames, sstride, fstride, T, st))) return rc;
+        } else if (c->resize_mode == 1) {
             // one warp per (frame, destination row, group of <= 32 destination columns)
             int nq = (c->w + 31) / 32, dxw = (c->w + nq - 1) / nq;
             int segpitch = ((c->W * 3 + nq - 1) / nq + 3 * (c->xtab.max_taps + 10) + 32 + 15) & ~15;

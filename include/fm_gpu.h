@@ -60,6 +60,8 @@ typedef struct fm_config {
 #define FM_FLAG_NO_UMMA     8   /* never take the tcgen05 one-pass Gaussian (k_umma.cu); the mma.sync two-pass kernels instead */
 #define FM_FLAG_UMMA        32  /* take the tcgen05 one-pass Gaussian wherever it applies (3 <= k <= 97, w % 32 == 0); without
                                    either flag the library picks the faster path for the geometry (measured: DESIGN.md) */
+#define FM_FLAG_NO_ROWS     64  /* default (resize) mode: never take the row-per-lane INTER_AREA kernel (k_resize_rows.cu);
+                                   the warp-per-destination-row kernels instead (A/B testing) */
 
 /* Derived parameters, exactly as the reference computes them. */
 typedef struct fm_info {
