@@ -320,50 +320,61 @@ int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt
     for (int d0 = 0; d0 < h; d0 += D)          // the band's y weights are staged in 2 NR floats
         if (ystart[std::min(d0 + D, h)] - ystart[d0] > 2 * r->NR) { delete r; return FM_OK; }
     r->nbands = (h + D - 1) / D;
-    r->CX = std::max(1, std::min(rr_env("FM_K0_CX", 2), w));
-    const int dxu = std::max(r->CX, rr_env("FM_K0_DXU", 20));
-    r->NCHU = std::max(1, (dxu + r->CX / 2) / r->CX);
-    const int DXU = r->CX * r->NCHU;
-    r->segs = (w + DXU - 1) / DXU;
-    // columns: groups of 4 consecutive source pixels from the first tap on, zero-weight padded at the end
-    std::vector<int4> col(w);                  // + one padding entry below
+    // columns per chunk: two when the CTA then still fits four to an SM (the measured optimum at 1080p -> 100: A/B log in
+    // profiles/), else one (large ratios: a chunk of two columns would take > 56 KB); FM_K0_CX / FM_K0_DXU override (tuning)
+    std::vector<int4> col;
     std::vector<float4> rw;
     std::vector<int> cstartw;
-    int BW = 16;
-    const int nchunks = (w + r->CX - 1) / r->CX;
-    for (int ch = 0; ch < nchunks; ch++) {
-        const int dxa = ch * r->CX, dxb = std::min(dxa + r->CX, w);
-        const int cstart = (3 * xidx[xstart[dxa]]) & ~15;
-        cstartw.push_back(cstart / 4);
-        for (int dx = dxa; dx < dxb; dx++) {
-            const int a = xstart[dx], b = xstart[dx + 1], first = xidx[a], nt = b - a;
-            for (int q = a; q < b; q++)
-                if (xidx[q] != first + (q - a)) { delete r; return FM_OK; }      // taps are consecutive pixels (always, for INTER_AREA)
-            const int ng = (nt + 3) / 4, off = 3 * first - cstart;
-            col[dx] = make_int4(off, ng, (int)rw.size(), 0);
-            for (int g = 0; g < ng; g++) {
-                float wv[4];
-                for (int i = 0; i < 4; i++) wv[i] = (4 * g + i < nt) ? xwt[a + 4 * g + i] : 0.0f;
-                rw.push_back(make_float4(wv[0], wv[1], wv[2], wv[3]));
-                rw.push_back(make_float4(-8388608.0f * wv[0], -8388608.0f * wv[1], -8388608.0f * wv[2], -8388608.0f * wv[3]));
-            }
-            // 16-byte blocks the passes of this column read: block (off >> 4) + ((WO + 3 npg) >> 2) of the last pass
-            for (int g0 = 0; g0 < ng; g0 += RR_GMAX) {
-                const int o = off + 12 * g0, npg = std::min(RR_GMAX, ng - g0);
-                const int last = (o >> 4) + ((((o >> 2) & 3) + 3 * npg) >> 2);
-                BW = std::max(BW, 16 * (last + 1));
+    auto layout = [&](int cx) -> bool {       // fills r, col, rw, cstartw for chunks of cx columns; false: does not fit
+        col.assign(w, make_int4(0, 0, 0, 0)); rw.clear(); cstartw.clear();
+        r->CX = cx;
+        const int dxu = std::max(cx, rr_env("FM_K0_DXU", 20));
+        r->NCHU = std::max(1, (dxu + cx / 2) / cx);
+        const int DXU = cx * r->NCHU;
+        r->segs = (w + DXU - 1) / DXU;
+        int BW = 16;
+        const int nchunks = (w + cx - 1) / cx;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int dxa = ch * cx, dxb = std::min(dxa + cx, w);
+            const int cstart = (3 * xidx[xstart[dxa]]) & ~15;
+            cstartw.push_back(cstart / 4);
+            for (int dx = dxa; dx < dxb; dx++) {
+                const int a = xstart[dx], b = xstart[dx + 1], first = xidx[a], nt = b - a;
+                for (int q = a; q < b; q++)
+                    if (xidx[q] != first + (q - a)) return false;              // taps are consecutive pixels (always, for INTER_AREA)
+                // groups of 4 consecutive source pixels from the first tap on, zero-weight padded at the end
+                const int ng = (nt + 3) / 4, off = 3 * first - cstart;
+                col[dx] = make_int4(off, ng, (int)rw.size(), 0);
+                for (int g = 0; g < ng; g++) {
+                    float wv[4];
+                    for (int i = 0; i < 4; i++) wv[i] = (4 * g + i < nt) ? xwt[a + 4 * g + i] : 0.0f;
+                    rw.push_back(make_float4(wv[0], wv[1], wv[2], wv[3]));
+                    rw.push_back(make_float4(-8388608.0f * wv[0], -8388608.0f * wv[1], -8388608.0f * wv[2], -8388608.0f * wv[3]));
+                }
+                // 16-byte blocks the passes of this column read: block (off >> 4) + ((WO + 3 npg) >> 2) of the last pass
+                for (int g0 = 0; g0 < ng; g0 += RR_GMAX) {
+                    const int o = off + 12 * g0, npg = std::min(RR_GMAX, ng - g0);
+                    const int last = (o >> 4) + ((((o >> 2) & 3) + 3 * npg) >> 2);
+                    BW = std::max(BW, 16 * (last + 1));
+                }
             }
         }
+        col.push_back(col.back());                                              // the kernel reads one entry ahead
+        if ((BW / 16) % 2 == 0) BW += 16;      // odd number of 16-byte blocks per row: conflict-free 128-bit loads down a column of rows
+        if (BW / 4 > 256) return false;        // TMA box limit
+        r->BW = BW;
+        r->stage_stride = (uint32_t)(((size_t)r->NR * BW + 127) / 128 * 128);
+        r->smem = 2 * (size_t)r->stage_stride + ((size_t)2 * cx * 3 * r->NRp + 2 * r->NR) * sizeof(float) + 8 + 16 +
+                  (size_t)r->D * DXU * 3;
+        return r->smem <= 200 * 1024;
+    };
+    {
+        const int forced = rr_env("FM_K0_CX", 0);
+        bool ok = false;
+        if (forced > 0) ok = layout(std::min(forced, w));
+        else ok = (w >= 2 && layout(2) && r->smem <= 56 * 1024) || layout(1);
+        if (!ok) { delete r; return FM_OK; }
     }
-    col.push_back(col.back());                                                  // the kernel reads one entry / one group ahead
-    rw.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); rw.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
-    if ((BW / 16) % 2 == 0) BW += 16;          // odd number of 16-byte blocks per row: conflict-free 128-bit loads down a column of rows
-    if (BW / 4 > 256) { delete r; return FM_OK; }      // TMA box limit
-    r->BW = BW;
-    r->stage_stride = (uint32_t)(((size_t)r->NR * BW + 127) / 128 * 128);
-    r->smem = 2 * (size_t)r->stage_stride + ((size_t)2 * r->CX * 3 * r->NRp + 2 * r->NR) * sizeof(float) + 8 + 16 +
-              (size_t)r->D * DXU * 3;
-    if (r->smem > 200 * 1024) { delete r; return FM_OK; }
     if (!rr_upload(&r->coltab, col) || !rr_upload(&r->cstartw, cstartw) || !rr_upload(&r->rw, rw)) {
         cudaFree(r->coltab); cudaFree(r->cstartw); cudaFree(r->rw);
         delete r;
