@@ -35,6 +35,18 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.fm_info) == 48
 
 
+def test_flag_values_match_header():
+    """The Python binding's FLAG_* constants are the header's FM_FLAG_* values (a maintainer's own stub copies the header)."""
+    from find_motion_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fm_gpu.h")).read()
+    flags = dict(re.findall(r"#define\s+FM_FLAG_([A-Z_]+)\s+(\d+)", hdr))
+    assert set(flags) >= {"KEEP_PLANES", "NO_FUSED", "NO_UMMA", "UMMA_APRON", "UMMA", "NO_ROWS"}
+    for name, val in flags.items():
+        assert getattr(_lib, "FLAG_" + name) == int(val), name
+    vals = [int(v) for v in flags.values()]
+    assert len(set(vals)) == len(vals) and all(v & (v - 1) == 0 for v in vals), "flags are distinct single bits"
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
