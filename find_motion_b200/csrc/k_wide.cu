@@ -19,6 +19,9 @@
 //   (ldmatrix.x4 = two column blocks).  The columns of a block are permuted (block nb holds columns
 //   8t' + 2nb + e) so that a thread ends up with 8 consecutive output bytes of a row: mask, two 32-bit stores.
 //   The planes stream through a cp.async double buffer along a strip of column tiles.
+#include <cuda.h>
+
+#include <cstdlib>
 #include <type_traits>
 
 #include "fm_common.cuh"
@@ -51,6 +54,31 @@ __device__ __forceinline__ void wimma0(int (&d)[4], uint32_t a0, uint32_t a1, ui
 __device__ __forceinline__ void wcp_async16(uint32_t dst, const void *src, bool valid) {
     const int n = valid ? 16 : 0;                 // src-size 0: the 16 bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+// mbarrier + TMA primitives (sm_100a PTX) of the TMA-staged pass 1
+__device__ __forceinline__ void wmbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wsmem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void wmbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wsmem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wmbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WH_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WH_WAIT_DONE;\n"
+        "bra WH_WAIT_LOOP;\n"
+        "WH_WAIT_DONE:\n"
+        "}\n" ::"r"(wsmem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void wtma_load_4d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(wsmem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
 struct WideGeom {
@@ -151,21 +179,26 @@ __device__ __forceinline__ uint32_t wgray4(uint32_t w0, uint32_t w1, uint32_t w2
     return __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);
 }
 
-// grid: (ceil(w / 256), NGa, F), 256 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
-// BGR: src = the caller's frames (identity resize, 16-byte aligned rows); otherwise src = the gray plane [F][h][w].
+// BORDER_REFLECT_101 columns of a staged window from their mirror images inside the window (one reflection)
+__device__ __forceinline__ void wide_h_mirror(unsigned char *tile, int X0, int w, int r, int R16, int pitch) {
+    const int tid = threadIdx.x;
+    const int nl = X0 == 0 ? R16 : 0;                    // shared columns [0, nl) are x < 0
+    const int c0 = w - X0 + R16;                         // shared column of x = w
+    const int nr = X0 + WH_COLS + r > w ? r : 0;
+    for (int i = tid; i < 32 * (nl + nr); i += WH_THREADS) {
+        const int rr = i / (nl + nr), j = i - rr * (nl + nr);
+        const int c = j < nl ? j : c0 + (j - nl);
+        const int cm = j < nl ? 2 * R16 - c : 2 * (c0 - 1) - c;      // x -> -x, x -> 2w - 2 - x
+        tile[rr * pitch + c] = tile[rr * pitch + cm];
+    }
+}
+
+// ---- pass 1, step A: stage the gray window of a CTA (shared column cc <-> image column X0 - R16 + cc, reflected; row rr <->
+// padded row 32 G + rr) with register-staged global loads.  BGR: the BGR -> gray conversion is fused in. ----
 template <bool BGR>
-__global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
-                                                       uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
-                                                       const uint2 *__restrict__ tabg, int w, int h, int r, int R16, int Sh,
-                                                       int pitch, int NGa, const int *__restrict__ nvalid) {
-    extern __shared__ __align__(16) unsigned char wsm[];
-    unsigned char *tile = wsm;                                              // [32][pitch] gray bytes
-    uint2 *tab = reinterpret_cast<uint2 *>(wsm + 32 * pitch);             // [4 Sh + 3][32]
+__device__ __forceinline__ void wide_h_stage(unsigned char *tile, const uint8_t *__restrict__ src, size_t sstride, size_t fstride,
+                                             int T, int f, int G, int X0, int w, int h, int r, int R16, int pitch) {
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-    const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
-    if (f % T >= __ldg(nvalid + f / T)) return;                             // not a real frame of this (ragged) call
-    for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
-    // stage the window: shared column cc <-> image column X0 - R16 + cc (reflected), row rr <-> padded row 32 G + rr
     if (BGR) {
         // warp wq: rows wq, wq+8, wq+16, wq+24; lane: a unit of 16 pixels = 48 BGR bytes (three 128-bit loads); the
         // loads of the four rows are issued before the first conversion
@@ -206,15 +239,7 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restr
         }
         if (mirror && (X0 == 0 || X0 + WH_COLS + r > w)) {       // BORDER_REFLECT_101 columns from their mirror images
             __syncthreads();
-            const int nl = X0 == 0 ? R16 : 0;                    // shared columns [0, nl) are x < 0
-            const int c0 = w - X0 + R16;                         // shared column of x = w
-            const int nr = X0 + WH_COLS + r > w ? r : 0;
-            for (int i = tid; i < 32 * (nl + nr); i += WH_THREADS) {
-                const int rr = i / (nl + nr), j = i - rr * (nl + nr);
-                const int c = j < nl ? j : c0 + (j - nl);
-                const int cm = j < nl ? 2 * R16 - c : 2 * (c0 - 1) - c;      // x -> -x, x -> 2w - 2 - x
-                tile[rr * pitch + c] = tile[rr * pitch + cm];
-            }
+            wide_h_mirror(tile, X0, w, r, R16, pitch);
         }
     } else {
         const int words = pitch >> 2;
@@ -237,7 +262,12 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restr
             }
         }
     }
-    __syncthreads();
+}
+
+// ---- pass 1, step B: the banded products of the staged window and the byte planes ----
+__device__ __forceinline__ void wide_h_products(const unsigned char *tile, const uint2 *tab, int f, int G, int X0, int w, int Sh,
+                                                int pitch, int NGa, uint32_t *__restrict__ plo, uint32_t *__restrict__ phi) {
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     if (X0 + 32 * wq >= w) return;                            // this warp's 32 columns are outside the image
     int acc[2][4][4];
     const uint32_t abase = wsmem_u32(tile) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * pitch + 32 * wq + 16 * (lane >> 4);
@@ -276,6 +306,85 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restr
                 qh[(8 * nb + e) * 4] = __byte_perm(p, q, 0x7632);
             }
         }
+}
+
+// grid: (ceil(w / 256), NGa, F), 256 threads.  dynamic smem: 32 * pitch + (4 Sh + 3) * 256
+// BGR: src = the caller's frames (identity resize, 16-byte aligned rows); otherwise src = the gray plane [F][h][w].
+template <bool BGR>
+__global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h(const uint8_t *__restrict__ src, size_t sstride, size_t fstride, int T,
+                                                       uint32_t *__restrict__ plo, uint32_t *__restrict__ phi,
+                                                       const uint2 *__restrict__ tabg, int w, int h, int r, int R16, int Sh,
+                                                       int pitch, int NGa, const int *__restrict__ nvalid) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    unsigned char *tile = wsm;                                              // [32][pitch] gray bytes
+    uint2 *tab = reinterpret_cast<uint2 *>(wsm + 32 * pitch);             // [4 Sh + 3][32]
+    const int tid = threadIdx.x;
+    const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
+    if (f % T >= __ldg(nvalid + f / T)) return;                             // not a real frame of this (ragged) call
+    for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
+    wide_h_stage<BGR>(tile, src, sstride, fstride, T, f, G, X0, w, h, r, R16, pitch);
+    __syncthreads();
+    wide_h_products(tile, tab, f, G, X0, w, Sh, pitch, NGa, plo, phi);
+}
+
+// The same pass with the BGR window staged by TMA (16-byte aligned frames, one-reflection borders): one thread issues one or two
+// boxes of 32 rows x (ubox units of 16 pixels = 48 bytes) for the whole CTA, every lane then converts units out of shared memory
+// (no per-thread global addresses, no idle lanes: 22 units per row at k = 97 left 10 of 32 lanes without work above).  Row groups
+// that touch the top or bottom border need reflected rows and take the register-staged path.
+// dynamic smem: nbox * 32 * ubox * 48 (raw BGR)  +  32 * pitch  +  (4 Sh + 3) * 256  +  16
+__global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ src,
+                                                           size_t sstride, size_t fstride, int T, uint32_t *__restrict__ plo,
+                                                           uint32_t *__restrict__ phi, const uint2 *__restrict__ tabg, int w, int h,
+                                                           int r, int R16, int Sh, int pitch, int NGa,
+                                                           const int *__restrict__ nvalid, int nunits, int ubox, int nbox) {
+    extern __shared__ __align__(128) unsigned char wsmt[];
+    const int boxbytes = 32 * ubox * 48;                                     // a multiple of 128
+    unsigned char *raw = wsmt;                                               // [nbox][32][ubox * 48] staged BGR rows
+    unsigned char *tile = raw + nbox * boxbytes;                             // [32][pitch] gray bytes
+    uint2 *tab = reinterpret_cast<uint2 *>(tile + 32 * pitch);              // [4 Sh + 3][32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tab + (4 * Sh + 3) * 32);
+    const int tid = threadIdx.x;
+    const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
+    if (f % T >= __ldg(nvalid + f / T)) return;                             // not a real frame of this (ragged) call
+    const int y0 = 32 * G - r;                                               // image row of the window's first row
+    const bool interior = y0 >= 0 && y0 + 32 <= h;                           // CTA-uniform
+    if (interior && tid == 0) {
+        wmbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        wmbar_expect_tx(bar, (uint32_t)(nbox * boxbytes));
+        const int c0 = (3 * (X0 - R16)) / 4;                                 // u32 column (negative / past the row: zero-filled)
+        for (int b = 0; b < nbox; b++) wtma_load_4d(wsmem_u32(raw) + b * boxbytes, &tmap, bar, c0 + b * ubox * 12, y0, f % T, f / T);
+    }
+    for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
+    if (interior) {
+        __syncthreads();                                                     // the barrier is initialised for everybody
+        wmbar_wait(bar, 0);
+        const int xneed = min(X0 + WH_COLS, w) + r;                          // first column no output of this CTA reads
+        const uint32_t inv = (65536u + nunits - 1) / nunits;                 // u / nunits == (u * inv) >> 16 for u * nunits < 65536
+        for (int u = tid; u < 32 * nunits; u += WH_THREADS) {
+            const int rr = (int)(((uint32_t)u * inv) >> 16), j = u - rr * nunits;
+            const int x = X0 - R16 + 16 * j;
+            if (x < 0 || x >= w || x >= xneed) continue;                     // border columns come from their mirror images below
+            const int jb = j >= ubox ? 1 : 0;
+            const uint4 *q = reinterpret_cast<const uint4 *>(raw + jb * boxbytes + rr * (ubox * 48) + (j - jb * ubox) * 48);
+            const uint4 r0 = q[0], r1 = q[1], r2 = q[2];
+            uint4 o;
+            o.x = wgray4(r0.x, r0.y, r0.z);
+            o.y = wgray4(r0.w, r1.x, r1.y);
+            o.z = wgray4(r1.z, r1.w, r2.x);
+            o.w = wgray4(r2.y, r2.z, r2.w);
+            *reinterpret_cast<uint4 *>(tile + rr * pitch + 16 * j) = o;
+        }
+        if (X0 == 0 || X0 + WH_COLS + r > w) {
+            __syncthreads();
+            wide_h_mirror(tile, X0, w, r, R16, pitch);
+        }
+    } else {
+        wide_h_stage<true>(tile, src, sstride, fstride, T, f, G, X0, w, h, r, R16, pitch);
+    }
+    __syncthreads();
+    wide_h_products(tile, tab, f, G, X0, w, Sh, pitch, NGa, plo, phi);
 }
 
 // shared slot of column c of a 32-column tile: the 8 columns {8t' + 2nb + e} of a block land in 8 different 16-byte lanes
@@ -613,6 +722,11 @@ int fm_launch_bg_export_wide(fm_ctx *c, int stream, double *dst_dev, cudaStream_
     return FM_OK;
 }
 
+typedef CUresult (*PFN_encodeTiledW)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiledW fm_tma_encoder();      // k_fused.cu
+
 // identity-resize gray plane (parity tap of the fused conversion), defined in k_frontend.cu
 int fm_launch_gray_plane(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 
@@ -658,8 +772,32 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
             int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
             if (rc) return rc;
         }
-        k_wide_h<true><<<hgrid, WH_THREADS, smh, st>>>(frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
-                                                       g.Sh, g.pitch, g.NGa, c->nvalid);
+        // TMA-staged pass 1 when the window of a CTA is one or two boxes and the CTA still fits four to an SM (k <= ~129)
+        const bool mirror = g.R16 < c->w && g.R16 + g.r < WH_COLS;
+        const int nunits = (g.R16 + WH_COLS + g.r + 15) / 16;
+        const int nbox = nunits > 21 ? 2 : 1, ubox = (nunits + nbox - 1) / nbox;
+        const size_t smt = (size_t)nbox * 32 * ubox * 48 + smh + 16;
+        static const long tma_kb = getenv("FM_WIDE_TMA_KB") ? atol(getenv("FM_WIDE_TMA_KB")) : 56;
+        if (mirror && ubox <= 21 && smt <= (size_t)tma_kb * 1024) {
+            PFN_encodeTiledW enc = fm_tma_encoder();
+            if (!enc) { fm_set_error("cuTensorMapEncodeTiled not available"); return FM_ECUDA; }
+            CUtensorMap tmap;      // the call's frames as a 4-D u32 tensor: (W*3/4 words, H rows, T frames, S streams)
+            cuuint64_t dims[4] = {(cuuint64_t)c->W * 3 / 4, (cuuint64_t)c->H, (cuuint64_t)T, (cuuint64_t)c->S};
+            cuuint64_t strides[3] = {(cuuint64_t)c->W * 3, (cuuint64_t)(T > 1 ? fstride : (size_t)c->W * 3 * c->H),
+                                     (cuuint64_t)(c->S > 1 ? sstride : (T > 1 ? fstride * T : (size_t)c->W * 3 * c->H))};
+            cuuint32_t box[4] = {(cuuint32_t)(ubox * 12), 32, 1, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void *)frames, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { fm_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return FM_ECUDA; }
+            if ((rc = fm_ensure_smem((const void *)k_wide_h_tma, smt, c->cfg.device))) return rc;
+            k_wide_h_tma<<<hgrid, WH_THREADS, smt, st>>>(tmap, frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
+                                                         g.Sh, g.pitch, g.NGa, c->nvalid, nunits, ubox, nbox);
+        } else {
+            k_wide_h<true><<<hgrid, WH_THREADS, smh, st>>>(frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
+                                                           g.Sh, g.pitch, g.NGa, c->nvalid);
+        }
     } else {
         if (frames) {
             int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);

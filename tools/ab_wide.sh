@@ -10,6 +10,7 @@ done
 for r in 1 2; do
   for v in "$@"; do
     cp _ab/libfmgpu_$v.so find_motion_b200/libfmgpu.so; touch find_motion_b200/libfmgpu.so
+    if [[ $v == *100 ]]; then export FM_WIDE_TMA_KB=100; else unset FM_WIDE_TMA_KB; fi      # variants named *100: TMA-staged pass 1 for every k
     timeout 120 python bench.py --steps 10 --warmup 3 --min-seconds 1 --no-e2e --no-cpu-baseline --no-extras --blur-scale 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', $r, 'k97', d['value'], d['roofline']['groups_ms_per_step'])"
     timeout 120 python bench.py --steps 5 --warmup 3 --min-seconds 1 --no-e2e --no-cpu-baseline --no-extras --size 3840x2160 --streams 1 --frames 16 --ring 16 --blur-scale 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', $r, '4k-k193', d['value'], d['roofline']['groups_ms_per_step'])"
   done
