@@ -21,6 +21,7 @@
 //   The planes stream through a cp.async double buffer along a strip of column tiles.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h_tma(const __grid_const
                                                            size_t sstride, size_t fstride, int T, uint32_t *__restrict__ plo,
                                                            uint32_t *__restrict__ phi, const uint2 *__restrict__ tabg, int w, int h,
                                                            int r, int R16, int Sh, int pitch, int NGa,
-                                                           const int *__restrict__ nvalid, int nunits, int ubox, int nbox) {
+                                                           const int *__restrict__ nvalid, int nunits, int ubox, int nbox, int gp) {
     extern __shared__ __align__(128) unsigned char wsmt[];
     const int boxbytes = 32 * ubox * 48;                                     // a multiple of 128
     unsigned char *raw = wsmt;                                               // [nbox][32][ubox * 48] staged BGR rows
@@ -344,47 +345,61 @@ __global__ void __launch_bounds__(WH_THREADS, 4) k_wide_h_tma(const __grid_const
     uint2 *tab = reinterpret_cast<uint2 *>(tile + 32 * pitch);              // [4 Sh + 3][32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(tab + (4 * Sh + 3) * 32);
     const int tid = threadIdx.x;
-    const int f = blockIdx.z, G = blockIdx.y, X0 = blockIdx.x * WH_COLS;
+    const int f = blockIdx.z, X0 = blockIdx.x * WH_COLS;
     if (f % T >= __ldg(nvalid + f / T)) return;                             // not a real frame of this (ragged) call
-    const int y0 = 32 * G - r;                                               // image row of the window's first row
-    const bool interior = y0 >= 0 && y0 + 32 <= h;                           // CTA-uniform
-    if (interior && tid == 0) {
+    // the CTA walks gp consecutive row groups: the box of group i + 1 is requested as soon as the conversion of group i has
+    // consumed the raw stage, and lands while the products of group i run
+    const int Gbeg = blockIdx.y * gp, Gend = min(Gbeg + gp, NGa);
+    auto interior = [&](int G) { return 32 * G - r >= 0 && 32 * G - r + 32 <= h; };    // CTA-uniform
+    auto issue = [&](int G) {                  // one thread
+        wmbar_expect_tx(bar, (uint32_t)(nbox * boxbytes));
+        const int c0 = (3 * (X0 - R16)) / 4;                                 // u32 column (negative / past the row: zero-filled)
+        for (int b = 0; b < nbox; b++) wtma_load_4d(wsmem_u32(raw) + b * boxbytes, &tmap, bar, c0 + b * ubox * 12, 32 * G - r, f % T, f / T);
+    };
+    if (tid == 0) {
         wmbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        wmbar_expect_tx(bar, (uint32_t)(nbox * boxbytes));
-        const int c0 = (3 * (X0 - R16)) / 4;                                 // u32 column (negative / past the row: zero-filled)
-        for (int b = 0; b < nbox; b++) wtma_load_4d(wsmem_u32(raw) + b * boxbytes, &tmap, bar, c0 + b * ubox * 12, y0, f % T, f / T);
+        if (interior(Gbeg)) issue(Gbeg);
     }
     for (int i = tid; i < (4 * Sh + 3) * 32; i += WH_THREADS) tab[i] = __ldg(tabg + i);
-    if (interior) {
-        __syncthreads();                                                     // the barrier is initialised for everybody
-        wmbar_wait(bar, 0);
-        const int xneed = min(X0 + WH_COLS, w) + r;                          // first column no output of this CTA reads
-        const uint32_t inv = (65536u + nunits - 1) / nunits;                 // u / nunits == (u * inv) >> 16 for u * nunits < 65536
-        for (int u = tid; u < 32 * nunits; u += WH_THREADS) {
-            const int rr = (int)(((uint32_t)u * inv) >> 16), j = u - rr * nunits;
-            const int x = X0 - R16 + 16 * j;
-            if (x < 0 || x >= w || x >= xneed) continue;                     // border columns come from their mirror images below
-            const int jb = j >= ubox ? 1 : 0;
-            const uint4 *q = reinterpret_cast<const uint4 *>(raw + jb * boxbytes + rr * (ubox * 48) + (j - jb * ubox) * 48);
-            const uint4 r0 = q[0], r1 = q[1], r2 = q[2];
-            uint4 o;
-            o.x = wgray4(r0.x, r0.y, r0.z);
-            o.y = wgray4(r0.w, r1.x, r1.y);
-            o.z = wgray4(r1.z, r1.w, r2.x);
-            o.w = wgray4(r2.y, r2.z, r2.w);
-            *reinterpret_cast<uint4 *>(tile + rr * pitch + 16 * j) = o;
-        }
-        if (X0 == 0 || X0 + WH_COLS + r > w) {
+    __syncthreads();                                                         // the barrier is initialised for everybody
+    const int xneed = min(X0 + WH_COLS, w) + r;                              // first column no output of this CTA reads
+    const uint32_t inv = (65536u + nunits - 1) / nunits;                     // u / nunits == (u * inv) >> 16 for u * nunits < 65536
+    uint32_t phase = 0;
+    for (int G = Gbeg; G < Gend; G++) {
+        const bool more = G + 1 < Gend && interior(G + 1);
+        if (interior(G)) {
+            wmbar_wait(bar, phase);
+            phase ^= 1;
+            for (int u = tid; u < 32 * nunits; u += WH_THREADS) {
+                const int rr = (int)(((uint32_t)u * inv) >> 16), j = u - rr * nunits;
+                const int x = X0 - R16 + 16 * j;
+                if (x < 0 || x >= w || x >= xneed) continue;                 // border columns come from their mirror images below
+                const int jb = j >= ubox ? 1 : 0;
+                const uint4 *q = reinterpret_cast<const uint4 *>(raw + jb * boxbytes + rr * (ubox * 48) + (j - jb * ubox) * 48);
+                const uint4 r0 = q[0], r1 = q[1], r2 = q[2];
+                uint4 o;
+                o.x = wgray4(r0.x, r0.y, r0.z);
+                o.y = wgray4(r0.w, r1.x, r1.y);
+                o.z = wgray4(r1.z, r1.w, r2.x);
+                o.w = wgray4(r2.y, r2.z, r2.w);
+                *reinterpret_cast<uint4 *>(tile + rr * pitch + 16 * j) = o;
+            }
+            __syncthreads();                                                 // raw stage consumed, window written
+            if (more && tid == 0) issue(G + 1);
+            if (X0 == 0 || X0 + WH_COLS + r > w) {
+                wide_h_mirror(tile, X0, w, r, R16, pitch);
+                __syncthreads();
+            }
+        } else {
+            wide_h_stage<true>(tile, src, sstride, fstride, T, f, G, X0, w, h, r, R16, pitch);
             __syncthreads();
-            wide_h_mirror(tile, X0, w, r, R16, pitch);
+            if (more && tid == 0) issue(G + 1);                              // the raw stage is not in use
         }
-    } else {
-        wide_h_stage<true>(tile, src, sstride, fstride, T, f, G, X0, w, h, r, R16, pitch);
+        wide_h_products(tile, tab, f, G, X0, w, Sh, pitch, NGa, plo, phi);
+        if (G + 1 < Gend) __syncthreads();                                   // every warp is done with the window
     }
-    __syncthreads();
-    wide_h_products(tile, tab, f, G, X0, w, Sh, pitch, NGa, plo, phi);
 }
 
 // shared slot of column c of a 32-column tile: the 8 columns {8t' + 2nb + e} of a block land in 8 different 16-byte lanes
@@ -792,8 +807,10 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) { fm_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return FM_ECUDA; }
             if ((rc = fm_ensure_smem((const void *)k_wide_h_tma, smt, c->cfg.device))) return rc;
-            k_wide_h_tma<<<hgrid, WH_THREADS, smt, st>>>(tmap, frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
-                                                         g.Sh, g.pitch, g.NGa, c->nvalid, nunits, ubox, nbox);
+            static const int gp = getenv("FM_WIDE_GP") ? std::max(1, atoi(getenv("FM_WIDE_GP"))) : 4;     // row groups per CTA (A/B: profiles/r2_wide_ab.txt)
+            dim3 tgrid(hgrid.x, (g.NGa + gp - 1) / gp, F);
+            k_wide_h_tma<<<tgrid, WH_THREADS, smt, st>>>(tmap, frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
+                                                         g.Sh, g.pitch, g.NGa, c->nvalid, nunits, ubox, nbox, gp);
         } else {
             k_wide_h<true><<<hgrid, WH_THREADS, smh, st>>>(frames, sstride, fstride, T, plo, phi, tabh, c->w, c->h, g.r, g.R16,
                                                            g.Sh, g.pitch, g.NGa, c->nvalid);
