@@ -787,12 +787,13 @@ int fm_launch_wide_blur(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t
             int rc = fm_launch_gray_plane(c, frames, sstride, fstride, T, st);
             if (rc) return rc;
         }
-        // TMA-staged pass 1 when the window of a CTA is one or two boxes and the CTA still fits four to an SM (k <= ~129)
+        // TMA-staged pass 1 when the window of a CTA is one or two boxes and the CTA needs <= 100 KB (k <= ~200 at 1080p / 4K: k = 97 runs four CTAs
+        // per SM, k = 193 three; measured against the register-staged path in profiles/r2_wide_ab.txt)
         const bool mirror = g.R16 < c->w && g.R16 + g.r < WH_COLS;
         const int nunits = (g.R16 + WH_COLS + g.r + 15) / 16;
         const int nbox = nunits > 21 ? 2 : 1, ubox = (nunits + nbox - 1) / nbox;
         const size_t smt = (size_t)nbox * 32 * ubox * 48 + smh + 16;
-        static const long tma_kb = getenv("FM_WIDE_TMA_KB") ? atol(getenv("FM_WIDE_TMA_KB")) : 56;
+        static const long tma_kb = getenv("FM_WIDE_TMA_KB") ? atol(getenv("FM_WIDE_TMA_KB")) : 100;
         if (mirror && ubox <= 21 && smt <= (size_t)tma_kb * 1024) {
             PFN_encodeTiledW enc = fm_tma_encoder();
             if (!enc) { fm_set_error("cuTensorMapEncodeTiled not available"); return FM_ECUDA; }
