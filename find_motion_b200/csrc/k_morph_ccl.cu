@@ -1008,7 +1008,9 @@ static int ccl_run(const CclScratch &sc, const uint32_t *plane, uint32_t *fill, 
             if (rc) return rc;
             k_ccl_frame_smem<<<nf, CCL2_THREADS, smem, st>>>(a, heavy);
             FM_LAUNCH_CHECK();
-            k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);          // idle unless a frame overflowed the shared tables
+            // the global-memory kernel takes the frames that overflowed the shared tables; on small planes (default mode:
+            // 100 x 56) no frame can hold more than CCL2_CAP runs of either polarity, and the idle launch is left out
+            if ((size_t)h * (w / 2 + 2) > CCL2_CAP) k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, heavy);
         } else {
             a.raw = nullptr;
             k_ccl_frame<<<nf, CCL_THREADS, 0, st>>>(a, nullptr);
