@@ -43,6 +43,11 @@ class fm_component(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("area_x2", "x", "y", "w", "h")]
 
 
+class fm_rows_plan_info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("usable", "band_rows", "box_rows", "chunk_cols", "seg_cols", "box_bytes",
+                                         "smem_bytes", "bands", "segs", "max_groups")]
+
+
 FLAG_KEEP_PLANES = 1
 FLAG_NO_FUSED = 2
 FLAG_NO_UMMA = 8
@@ -74,6 +79,7 @@ SYMBOLS = {
     "fm_debug_mask": (C.c_int, [_P, C.c_int, _P]),
     "fm_debug_components": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(fm_component), C.POINTER(C.c_int)]),
     "fm_resize_area": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
+    "fm_debug_rows_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(fm_rows_plan_info)]),
     "fm_launch_count": (C.c_uint64, []),
     "fm_timing_enable": (C.c_int, [_P, C.c_int]),
     "fm_timing_reset": (C.c_int, [_P]),

@@ -161,6 +161,8 @@ int fm_launch_resize_bgr(int device, const uint8_t *src_dev, int W, int H, int w
                          const ResizeTab &xt, const ResizeTab &yt, uint8_t *dst_dev, cudaStream_t st);
 int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt, const int *ystart, const int *yidx);
 void fm_rows_free(fm_ctx *c);
+int fm_rows_plan_describe(int W, int w, int h, const int *xstart, const int *xidx, const float *xwt, const int *ystart,
+                          const int *yidx, fm_rows_plan_info *out);
 bool fm_rows_usable(const fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride);
 int fm_launch_resize_rows(fm_ctx *c, const uint8_t *frames, size_t sstride, size_t fstride, int T, cudaStream_t st);
 bool fm_umma_supported(const fm_ctx *c);

@@ -716,6 +716,17 @@ extern "C" int fm_debug_mask(fm_ctx *c, int stream, uint8_t *mask) {
 }
 
 // find_objects' input plane (find_motion.py:703-706): imutils.resize(frame.raw, width=300) = INTER_AREA, BGR out
+extern "C" int fm_debug_rows_plan(int W, int H, int box_size, fm_rows_plan_info *info) {
+    if (!info || W < 1 || H < 1 || box_size < 1 || box_size > W) { fm_set_error("bad geometry"); return FM_EINVAL; }
+    const int w = box_size, h = (int)((double)H * ((double)box_size / (double)W));          // imutils.resize
+    memset(info, 0, sizeof(*info));
+    if (h < 1 || (w == W && h == H)) return FM_OK;
+    const double sx = 1.0 / ((double)w / W), sy = 1.0 / ((double)h / H);
+    if (fabs(sx - nearbyint(sx)) < 2.220446049250313e-16 && fabs(sy - nearbyint(sy)) < 2.220446049250313e-16) return FM_OK;   // integer ratio
+    const HostTab xt = area_tab(W, w), yt = area_tab(H, h);
+    return fm_rows_plan_describe(W, w, h, xt.start.data(), xt.idx.data(), xt.wt.data(), yt.start.data(), yt.idx.data(), info);
+}
+
 extern "C" int fm_resize_area(int device, const uint8_t *bgr_host, int W, int H, int width, uint8_t *out_host, int *out_height) {
     if (!bgr_host || !out_host || W < 1 || H < 1 || width < 1) { fm_set_error("bad argument"); return FM_EINVAL; }
     if (width > W) { fm_set_error("width %d > frame width %d: upscaling resize is not supported", width, W); return FM_ERANGE; }

@@ -290,12 +290,13 @@ static int rr_env(const char *name, int dflt) {
     return (e && *e) ? atoi(e) : dflt;
 }
 
-// Builds the plan of the rows kernel for the context's decimation tables; leaves c->rows null (the warp-per-row kernels
-// stay in charge) when the geometry does not fit: source rows not TMA-compatible, bands taller than the CTA, tiny ratios.
-int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt, const int *ystart, const int *yidx) {
-    c->rows = nullptr;
-    if ((c->cfg.flags & FM_FLAG_NO_ROWS) || ((size_t)c->W * 3) % 16 != 0) return FM_OK;
-    const int w = c->w, h = c->h;
+// Host arithmetic of the plan (no CUDA): fills r and the three tables for the decimation tables of a geometry.  false: the
+// geometry does not fit the kernel (source rows not TMA-compatible, bands taller than the CTA, tiny ratios) and the
+// warp-per-row kernels stay in charge.
+static bool rr_layout(int W, int w, int h, const int *xstart, const int *xidx, const float *xwt, const int *ystart,
+                      const int *yidx, RowsPlan *r, std::vector<int4> &col, std::vector<float4> &rw, std::vector<int> &cstartw) {
+    memset(r, 0, sizeof(*r));
+    if (((size_t)W * 3) % 16 != 0) return false;
     // band height: the most destination rows whose source rows fit the CTA
     auto band_rows = [&](int D) {
         int mx = 0;
@@ -309,22 +310,17 @@ int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt
     for (int d = 1; d <= h; d++) {
         if (band_rows(d) <= RR_THREADS) D = d; else break;
     }
-    if (D == 0) return FM_OK;
+    if (D == 0) return false;
     // tiny ratios (a handful of taps per cell) are not what this kernel is for
     int max_xt = 0;
     for (int dx = 0; dx < w; dx++) max_xt = std::max(max_xt, xstart[dx + 1] - xstart[dx]);
-    if (max_xt < 4) return FM_OK;
-    RowsPlan *r = new RowsPlan();
-    memset(r, 0, sizeof(*r));
+    if (max_xt < 4) return false;
     r->D = D; r->NR = band_rows(D); r->NRp = r->NR | 1;
     for (int d0 = 0; d0 < h; d0 += D)          // the band's y weights are staged in 2 NR floats
-        if (ystart[std::min(d0 + D, h)] - ystart[d0] > 2 * r->NR) { delete r; return FM_OK; }
+        if (ystart[std::min(d0 + D, h)] - ystart[d0] > 2 * r->NR) return false;
     r->nbands = (h + D - 1) / D;
     // columns per chunk: two when the CTA then still fits four to an SM (the measured optimum at 1080p -> 100: A/B log in
     // profiles/), else one (large ratios: a chunk of two columns would take > 56 KB); FM_K0_CX / FM_K0_DXU override (tuning)
-    std::vector<int4> col;
-    std::vector<float4> rw;
-    std::vector<int> cstartw;
     auto layout = [&](int cx) -> bool {       // fills r, col, rw, cstartw for chunks of cx columns; false: does not fit
         col.assign(w, make_int4(0, 0, 0, 0)); rw.clear(); cstartw.clear();
         r->CX = cx;
@@ -368,13 +364,21 @@ int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt
                   (size_t)r->D * DXU * 3;
         return r->smem <= 200 * 1024;
     };
-    {
-        const int forced = rr_env("FM_K0_CX", 0);
-        bool ok = false;
-        if (forced > 0) ok = layout(std::min(forced, w));
-        else ok = (w >= 2 && layout(2) && r->smem <= 56 * 1024) || layout(1);
-        if (!ok) { delete r; return FM_OK; }
-    }
+    const int forced = rr_env("FM_K0_CX", 0);
+    if (forced > 0) return layout(std::min(forced, w));
+    return (w >= 2 && layout(2) && r->smem <= 56 * 1024) || layout(1);
+}
+
+// Builds the plan of the rows kernel for the context's decimation tables; leaves c->rows null when the geometry does not fit
+// (rr_layout) or FM_FLAG_NO_ROWS is set.
+int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt, const int *ystart, const int *yidx) {
+    c->rows = nullptr;
+    if (c->cfg.flags & FM_FLAG_NO_ROWS) return FM_OK;
+    RowsPlan *r = new RowsPlan();
+    std::vector<int4> col;
+    std::vector<float4> rw;
+    std::vector<int> cstartw;
+    if (!rr_layout(c->W, c->w, c->h, xstart, xidx, xwt, ystart, yidx, r, col, rw, cstartw)) { delete r; return FM_OK; }
     if (!rr_upload(&r->coltab, col) || !rr_upload(&r->cstartw, cstartw) || !rr_upload(&r->rw, rw)) {
         cudaFree(r->coltab); cudaFree(r->cstartw); cudaFree(r->rw);
         delete r;
@@ -383,6 +387,43 @@ int fm_rows_plan(fm_ctx *c, const int *xstart, const int *xidx, const float *xwt
     }
     c->rows = r;
     return fm_ensure_smem((const void *)k_resize_rows, r->smem, c->cfg.device);
+}
+
+// Plan of a geometry without a device (include/fm_gpu.h: fm_debug_rows_plan): the layout plus a re-check, tap by tap, that
+// every shared-memory read of every column pass stays inside the chunk's box and meets the weight the tables give it.
+int fm_rows_plan_describe(int W, int w, int h, const int *xstart, const int *xidx, const float *xwt, const int *ystart,
+                          const int *yidx, fm_rows_plan_info *out) {
+    RowsPlan r;
+    std::vector<int4> col;
+    std::vector<float4> rw;
+    std::vector<int> cstartw;
+    memset(out, 0, sizeof(*out));
+    if (!rr_layout(W, w, h, xstart, xidx, xwt, ystart, yidx, &r, col, rw, cstartw)) return FM_OK;
+    out->usable = 1;
+    out->band_rows = r.D; out->box_rows = r.NR; out->chunk_cols = r.CX; out->seg_cols = r.CX * r.NCHU;
+    out->box_bytes = r.BW; out->smem_bytes = (int32_t)r.smem; out->bands = r.nbands; out->segs = r.segs;
+    for (int dx = 0; dx < w; dx++) {
+        const int ch = dx / r.CX, a = xstart[dx], nt = xstart[dx + 1] - a;
+        const int4 ci = col[dx];
+        out->max_groups = std::max(out->max_groups, ci.y);
+        if (4 * cstartw[ch] + ci.x != 3 * xidx[a] || (cstartw[ch] & 3) || ci.x < 0) { fm_set_error("rows plan: column %d misplaced", dx); return FM_ERANGE; }
+        for (int g = 0; g < ci.y; g++)
+            for (int i = 0; i < 4; i++) {
+                const float wv = (&rw[ci.z + 2 * g].x)[i], nv = (&rw[ci.z + 2 * g + 1].x)[i];
+                const float want = 4 * g + i < nt ? xwt[a + 4 * g + i] : 0.0f;
+                if (wv != want || nv != -8388608.0f * want) { fm_set_error("rows plan: weight of column %d tap %d", dx, 4 * g + i); return FM_ERANGE; }
+                if (ci.x + 3 * (4 * g + i) + 2 >= r.BW) { fm_set_error("rows plan: column %d reads past the box", dx); return FM_ERANGE; }
+            }
+        for (int g0 = 0; g0 < ci.y; g0 += RR_GMAX) {           // the 128-bit loads of a pass
+            const int o = ci.x + 12 * g0, npg = std::min(RR_GMAX, ci.y - g0);
+            if (16 * ((o >> 4) + ((((o >> 2) & 3) + 3 * npg) >> 2) + 1) > r.BW) { fm_set_error("rows plan: pass of column %d reads past the box", dx); return FM_ERANGE; }
+        }
+    }
+    for (int b = 0; b < r.nbands; b++) {
+        const int d0 = b * r.D, d1 = std::min(d0 + r.D, h);
+        if (yidx[ystart[d1] - 1] - yidx[ystart[d0]] + 1 > r.NR || r.NR > RR_THREADS) { fm_set_error("rows plan: band %d taller than the box", b); return FM_ERANGE; }
+    }
+    return FM_OK;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

@@ -97,6 +97,19 @@ typedef struct fm_component {
     int32_t x, y, w, h;
 } fm_component;
 
+/* Plan of the default-mode resize kernel (k_resize_rows.cu) for one geometry: fm_debug_rows_plan. */
+typedef struct fm_rows_plan_info {
+    int32_t usable;        /* 0: the warp-per-row kernels take this geometry (rows not TMA-compatible, < 4 taps, band too tall) */
+    int32_t band_rows;     /* destination rows per CTA */
+    int32_t box_rows;      /* source rows of a TMA box (<= 160 = the CTA's row threads) */
+    int32_t chunk_cols;    /* destination columns per TMA box */
+    int32_t seg_cols;      /* destination columns per CTA */
+    int32_t box_bytes;     /* bytes per box row: an odd multiple of 16, <= 1024 */
+    int32_t smem_bytes;    /* dynamic shared memory per CTA */
+    int32_t bands, segs;   /* grid.y, grid.x */
+    int32_t max_groups;    /* most 4-pixel tap groups of a destination column */
+} fm_rows_plan_info;
+
 const char *fm_last_error(void);
 int fm_version(void);
 
@@ -185,6 +198,12 @@ int fm_debug_components(int device, const uint8_t *plane, int w, int h, int max_
  * out_host holds width * out_height * 3 bytes.  The detectors themselves stay on the host. */
 int fm_resize_area(int device, const uint8_t *bgr_host, int frame_width, int frame_height, int width,
                    uint8_t *out_host, int *out_height);
+
+/* Host-side test entry (no device needed): derives the processing plane and the INTER_AREA tables of a frame size and
+ * box_size exactly as fm_ctx_create does (find_motion.py:487-492), lays out the plan of the row-per-lane resize kernel and
+ * re-checks, tap by tap, that every read of every column stays inside its TMA box and meets the weight cv2's table gives
+ * it.  FM_OK with info->usable = 0 when the geometry is left to the warp-per-row kernels; FM_ERANGE if a check fails. */
+int fm_debug_rows_plan(int frame_width, int frame_height, int box_size, fm_rows_plan_info *info);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t fm_launch_count(void);
